@@ -1,0 +1,71 @@
+"""ctypes binding of the C-ABI library (include/excel_b200.h).
+
+The product path is CUDA only: if libexcel_b200.so is missing or a call fails this raises -- there is
+no CPU or PyTorch fallback behind any shim in this package.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libexcel_b200.so")
+
+_c = ctypes
+_i, _i64, _f, _p = _c.c_int, _c.c_int64, _c.c_float, _c.c_void_p
+
+# name -> argtypes; must list every symbol declared in include/excel_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "excel_last_error": ([], _c.c_char_p),
+    "excel_version": ([], _i),
+    "excel_device_arch": ([_i], _i),
+    "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p], _i),
+    "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"excel_b200: {LIB_PATH} is missing -- build it with `python -m excel_b200.build` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, res
+        _lib = L
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; non-zero -> RuntimeError with the library's message."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {L.excel_last_error().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("excel_b200: expected a CUDA tensor (the hot path has no CPU implementation)")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32c(t):
+    """fp32 + contiguous, like the reference's `.float()` calls (no copy when already so)."""
+    return t.detach().to(torch.float32).contiguous()
+
+
+def int_array(values):
+    return (ctypes.c_int * len(values))(*[int(v) for v in values])

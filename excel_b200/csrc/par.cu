@@ -1,0 +1,510 @@
+// PAR -- pixel-adaptive refinement (reference: utils/PAR.py) as HBM-roofline kernels for sm_100a.
+//
+//   par_affinity : img [B,3,H,W] -> aff [B,K,H,W]   (utils/PAR.py:67-86), K = 8 * n_dil
+//   par_iterate  : planes <- sum_k aff_k * planes[clamped neighbour k]   (utils/PAR.py:88-90)
+//   par_labels   : valid_key[argmax_c planes]                            (utils/affutils.py:86-87)
+//
+// Layout: every tensor is planar fp32, x fastest.  "Planes" are the mask channels of ALL images of
+// a batch packed back to back ([P,H,W], P = sum_b C_b); plane_off[b]..plane_off[b+1] are image b's
+// channels (C differs per image: background + present classes).
+//
+// Neighbour k = di*8 + t reads (clamp(y + DY[t]*d), clamp(x + DX[t]*d)), d = dilations[di]:
+// replicate padding + one-hot dilated 3x3 conv of the reference (utils/PAR.py:10-24,39-49).
+#include "common.cuh"
+#include "excel_b200.h"
+#include "ptx.cuh"
+
+namespace xl {
+
+struct ParGeom {
+    int n_dil;
+    int dil[XL_PAR_MAX_DIL];
+    float pos[8 * XL_PAR_MAX_DIL];  // w2 * softmax_k(-(pos_k/(std(pos)+1e-8)/w1)^2), utils/PAR.py:84-86
+};
+
+
+// ------------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=True (utils/PAR.py:67).  One thread per output pixel.
+__global__ void par_resize_ac_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int64_t sy,
+                                     float* __restrict__ dst, int hi, int wi, int H, int W) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int bc = blockIdx.z;  // b*3 + c
+    if (x >= W || y >= H) return;
+    const float ry = H > 1 ? (float)(hi - 1) / (float)(H - 1) : 0.f;
+    const float rx = W > 1 ? (float)(wi - 1) / (float)(W - 1) : 0.f;
+    const float fy = ry * y, fx = rx * x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+    const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = src + (int64_t)(bc / 3) * sb + (int64_t)(bc % 3) * sc;
+    const float v = hy * (hx * __ldg(p + y0 * sy + x0) + lx * __ldg(p + y0 * sy + x1)) +
+                    ly * (hx * __ldg(p + y1 * sy + x0) + lx * __ldg(p + y1 * sy + x1));
+    dst[((int64_t)bc * H + y) * W + x] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tiling shared by the two hot kernels: a block of 32x8 threads owns a TX x TY = 32x32 pixel tile
+// (4 rows per thread) and stages the tile plus a halo of max(dilation) pixels in shared memory with
+// the replicate padding already applied (coordinates clamped at load time), so the 8*n_dil gathers
+// per pixel are conflict-free LDS (a warp reads 32 consecutive floats) with no bounds logic.
+constexpr int kTX = 32, kTY = 32, kRows = 4;  // kTY == 8 * kRows
+
+__host__ __device__ constexpr int tap_dy(int t) { return t < 3 ? -1 : (t < 5 ? 0 : 1); }
+__host__ __device__ constexpr int tap_dx(int t) { return (t == 0 || t == 3 || t == 5) ? -1 : ((t == 1 || t == 6) ? 0 : 1); }
+
+// stage `nplanes` planes (plane p at src + p*plane_stride, rows `sy` apart) into sm[p][TH][TW] with
+// cp.async: every copy of the tile is in flight at once (one memory round trip instead of a chain of
+// register-staged loads); rows whose whole span is inside the image and 16 B-aligned move as 16 B
+// copies.  Called by the first 256 threads of the CTA (tid = 0..255); complete with
+// cp_async_wait_all() + a barrier.
+__device__ __forceinline__ void stage_tile_async(float* sm, const float* __restrict__ src, int64_t plane_stride, int64_t sy,
+                                                 int nplanes, int x0, int y0, int halo, int TW, int TH, int H, int W,
+                                                 int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int xl = x0 - halo;
+    const bool inside = xl >= 0 && xl + TW <= W;
+    for (int p = 0; p < nplanes; ++p) {
+        const float* sp = src + p * plane_stride;
+        float* dp = sm + p * TH * TW;
+        for (int r = warp; r < TH; r += 8) {
+            const float* row = sp + (int64_t)clampi(y0 - halo + r, 0, H - 1) * sy;
+            if (inside && ((reinterpret_cast<uintptr_t>(row + xl) & 15) == 0)) {
+                for (int c = lane * 4; c < TW; c += 128) cp_async16(dp + r * TW + c, row + xl + c);
+            } else {
+                for (int c = lane; c < TW; c += 32) cp_async4(dp + r * TW + c, row + clampi(xl + c, 0, W - 1));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Affinity (utils/PAR.py:67-86).  HBM traffic is the K output planes (192 B/pixel at K=48) against
+// 12 B/pixel of image; the image tile + halo is read from L2.
+//   pass 1: per channel, unbiased std of the K neighbours (centre excluded), accumulated on the
+//           differences to the centre pixel -- small where the image is smooth, so the one-pass
+//           sum / sum-of-squares form is well conditioned;
+//   pass 2: a_k = -mean_c[(|I_k - I_0| / (std_c + 1e-8) / w1)^2] kept in registers, softmax over k,
+//           + w2 * (constant positional softmax), streamed out with evict-first stores.
+template <int NDIL>
+__global__ void __launch_bounds__(256, 2)
+par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, float* __restrict__ aff,
+                    int H, int W, int Wp, int halo, ParGeom g, float w1) {
+    constexpr int K = 8 * NDIL;
+    extern __shared__ float sm[];
+    const int TW = kTX + 2 * halo, TH = kTY + 2 * halo;
+    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = blockIdx.z;
+    stage_tile_async(sm, img + (int64_t)b * sb, sc, sy, 3, x0, y0, halo, TW, TH, H, W, threadIdx.y * 32 + threadIdx.x);
+    cp_async_wait_all();
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= W) return;
+    const float* s0p = sm + (threadIdx.y + halo) * TW + threadIdx.x + halo;
+    const int cs = TH * TW;
+    const int64_t plane = (int64_t)H * Wp;  // the affinity workspace has a row pitch of Wp = round_up(W, 4)
+    const float invk = 1.f / K, invk1 = 1.f / (K - 1), invw = 1.f / w1;
+#pragma unroll 1
+    for (int j = 0; j < kRows; ++j) {
+        const int y = y0 + threadIdx.y + 8 * j;
+        if (y >= H) break;
+        const float* ctr = s0p + 8 * j * TW;
+        const float c0 = ctr[0], c1 = ctr[cs], c2 = ctr[2 * cs];
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int di = 0; di < NDIL; ++di) {
+            const int d = g.dil[di], dW = d * TW;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
+                const float d0 = p[0] - c0, d1 = p[cs] - c1, d2 = p[2 * cs] - c2;
+                s0 += d0; q0 = fmaf(d0, d0, q0);
+                s1 += d1; q1 = fmaf(d1, d1, q1);
+                s2 += d2; q2 = fmaf(d2, d2, q2);
+            }
+        }
+        const float r0 = invw / (sqrtf(fmaxf((q0 - s0 * s0 * invk) * invk1, 0.f)) + 1e-8f);
+        const float r1 = invw / (sqrtf(fmaxf((q1 - s1 * s1 * invk) * invk1, 0.f)) + 1e-8f);
+        const float r2 = invw / (sqrtf(fmaxf((q2 - s2 * s2 * invk) * invk1, 0.f)) + 1e-8f);
+        float a[K];
+        float amax = -INFINITY;
+#pragma unroll
+        for (int di = 0; di < NDIL; ++di) {
+            const int d = g.dil[di], dW = d * TW;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
+                const float t0 = fabsf(p[0] - c0) * r0, t1 = fabsf(p[cs] - c1) * r1, t2 = fabsf(p[2 * cs] - c2) * r2;
+                const float v = -(t0 * t0 + t1 * t1 + t2 * t2) / 3.f * 1.4426950408889634f;  // log2(e): exp2 below
+                a[di * 8 + t] = v;
+                amax = fmaxf(amax, v);
+            }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            a[k] = exp2f(a[k] - amax);
+            sum += a[k];
+        }
+        const float inv = 1.f / sum;
+        float* out = aff + ((int64_t)b * K * H + y) * Wp + x;
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k * plane] = fmaf(a[k], inv, g.pos[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One propagation step (utils/PAR.py:88-90): out[p,y,x] = sum_k aff[b,k,y,x] * in[p, nbr_k(y,x)].
+// Algorithmic bytes per pixel and step: 4*(K + 2*C); the K affinity planes are the stream.
+//
+//  * The affinity tile [K][32][32] is streamed by TMA (cp.async.bulk.tensor.3d) into a 2-stage shared
+//    ring of kG=4 taps (16 KB) per stage, completion on mbarriers: the loads are asynchronous, cost no
+//    registers or LSU issue slots, and with 2 CTAs/SM keep 64 KB in flight per SM (HBM needs ~35 KB).
+//    The affinity workspace is internal, so its row pitch is padded to 4 floats (TMA stride rule) and
+//    out-of-image elements are zero-filled by the TMA unit.
+//  * A thread owns 4 consecutive pixels of one row: affinities are one LDS.128, mask neighbours one
+//    LDS.128 per plane when the dilation is a multiple of 4 (4 of the 6 standard dilations), and a
+//    compile-time-shifted LDS.128/LDS.64/LDS.32 combination for dilations 1 and 2.
+//  * CCH mask planes (+ halo, replicate padding applied at load) are staged in shared memory; images
+//    with more planes loop (the affinity re-read then comes from L2).
+constexpr int kG = 2;        // taps per TMA stage (8 KB)
+constexpr int kStages = 4;   // ring depth: kStages-1 stages (24 KB per CTA, 48 KB per SM) in flight
+constexpr int kParThreads = 256 + 32;  // 8 consumer warps + 1 TMA producer warp
+
+template <int O>
+__device__ __forceinline__ void load4_shift(const float* p, float (&m)[4]) {
+    // m[i] = p[i + O] for a 16 B-aligned p
+    if constexpr (O == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    } else if constexpr (O == -1) {
+        const float l = p[-1];
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        m[0] = l; m[1] = v.x; m[2] = v.y; m[3] = v.z;
+    } else if constexpr (O == 1) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        const float r = p[4];
+        m[0] = v.y; m[1] = v.z; m[2] = v.w; m[3] = r;
+    } else if constexpr (O == -2) {
+        const float2 l = *reinterpret_cast<const float2*>(p - 2);
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        m[0] = l.x; m[1] = l.y; m[2] = v.x; m[3] = v.y;
+    } else {  // O == 2
+        const float2 v = *reinterpret_cast<const float2*>(p + 2);
+        const float2 r = *reinterpret_cast<const float2*>(p + 4);
+        m[0] = v.x; m[1] = v.y; m[2] = r.x; m[3] = r.y;
+    }
+}
+
+// MODE: 1 / 2 = dilation 1 / 2 (compile-time shifts); 0 = dilation % 4 == 0 (aligned LDS.128); -1 = any
+template <int CCH, int MODE, int T0>
+__device__ __forceinline__ void par_taps(const float* __restrict__ as, const float* __restrict__ ctr, int cs, int d, int dW,
+                                         float (&acc)[4][CCH]) {
+#pragma unroll
+    for (int tt = 0; tt < kG; ++tt) {
+        constexpr int dummy = 0; (void)dummy;
+        const int t = T0 + tt;
+        const float4 a4 = *reinterpret_cast<const float4*>(as + tt * kTY * kTX);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+        const int dy = tap_dy(t), dx = tap_dx(t);
+#pragma unroll
+        for (int c = 0; c < CCH; ++c) {
+            float m[4];
+            if constexpr (MODE == 1 || MODE == 2) {
+                const float* p = ctr + c * cs + dy * dW;
+                if (dx < 0) load4_shift<-MODE>(p, m);
+                else if (dx > 0) load4_shift<MODE>(p, m);
+                else load4_shift<0>(p, m);
+            } else if constexpr (MODE == 0) {
+                load4_shift<0>(ctr + c * cs + dy * dW + dx * d, m);
+            } else {
+                const float* p = ctr + c * cs + dy * dW + dx * d;
+                m[0] = p[0]; m[1] = p[1]; m[2] = p[2]; m[3] = p[3];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(a[i], m[i], acc[i][c]);
+        }
+    }
+}
+
+template <int CCH, int T0>
+__device__ __forceinline__ void par_taps_mode(int mode, const float* as, const float* ctr, int cs, int d, int dW,
+                                              float (&acc)[4][CCH]) {
+    if (mode == 0) par_taps<CCH, 0, T0>(as, ctr, cs, d, dW, acc);
+    else if (mode == 1) par_taps<CCH, 1, T0>(as, ctr, cs, d, dW, acc);
+    else if (mode == 2) par_taps<CCH, 2, T0>(as, ctr, cs, d, dW, acc);
+    else par_taps<CCH, -1, T0>(as, ctr, cs, d, dW, acc);
+}
+
+template <int CCH>
+__global__ void __launch_bounds__(kParThreads, 2)
+par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __restrict__ in, float* __restrict__ out,
+                   const int* __restrict__ plane_off, int img0, int H, int W, int halo, ParGeom g) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    // [kStages][kG][kTY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
+    float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    float* sm = ring + kStages * kG * kTY * kTX;
+    const int TW = kTX + 2 * halo, TH = kTY + 2 * halo, cs = TH * TW;
+    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = img0 + blockIdx.z;
+    const int tid = threadIdx.x;
+    const int K = 8 * g.n_dil, nchunk = K / kG;
+    const int64_t plane = (int64_t)H * W;
+    const int pbeg = plane_off[b], pend = plane_off[b + 1];
+    const int npass = (pend - pbeg + CCH - 1) / CCH;
+    const int total = npass * nchunk;
+    constexpr uint32_t kStageBytes = kG * kTY * kTX * sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (tid >= 256) {  // ---- producer warp: one lane streams the affinity chunks through the ring
+        if (tid == 256) {
+            for (int i = 0; i < total; ++i) {
+                const int s = i % kStages;
+                if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
+                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                tma_load_3d(ring + s * kG * kTY * kTX, &tm_aff, &full_bar[s], x0, y0,
+                            (int)blockIdx.z * K + (i % nchunk) * kG);
+            }
+        }
+        return;
+    }
+
+    // ---- consumers: thread (tx4, ty) owns pixels (y0+ty, x0+4*tx4 .. +3)
+    const int tx4 = tid & 7, ty = tid >> 3;
+    const float* ctr = sm + (ty + halo) * TW + 4 * tx4 + halo;
+    const float* as0 = ring + ty * kTX + 4 * tx4;
+    int it = 0;
+    for (int pc = pbeg; pc < pend; pc += CCH) {
+        const int np = min(CCH, pend - pc);
+        if (pc != pbeg) bar_sync(1, 256);
+        stage_tile_async(sm, in + (int64_t)pc * plane, plane, W, np, x0, y0, halo, TW, TH, H, W, tid);
+        cp_async_wait_all();
+        bar_sync(1, 256);
+        float acc[4][CCH];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
+#pragma unroll 1
+        for (int di = 0; di < g.n_dil; ++di) {
+            const int d = g.dil[di], dW = d * TW;
+            const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
+#pragma unroll
+            for (int q = 0; q < 8 / kG; ++q) {
+                const int s = it % kStages;
+                mbar_wait(&full_bar[s], (it / kStages) & 1);
+                const float* as = as0 + s * kG * kTY * kTX;
+                if (q == 0) par_taps_mode<CCH, 0 * kG>(mode, as, ctr, cs, d, dW, acc);
+                else if (q == 1) par_taps_mode<CCH, 1 * kG>(mode, as, ctr, cs, d, dW, acc);
+                else if (q == 2) par_taps_mode<CCH, 2 * kG>(mode, as, ctr, cs, d, dW, acc);
+                else par_taps_mode<CCH, 3 * kG>(mode, as, ctr, cs, d, dW, acc);
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with stage s
+                ++it;
+            }
+        }
+        const int y = y0 + ty, x = x0 + 4 * tx4;
+        if (y < H) {
+#pragma unroll
+            for (int c = 0; c < CCH; ++c) {
+                if (c >= np) break;
+                float* o = out + (int64_t)(pc + c) * plane + (int64_t)y * W + x;
+                if (x + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    *reinterpret_cast<float4*>(o) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (x + i < W) o[i] = acc[i][c];
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// labels[b,y,x] = key[plane_off[b] + argmax_c planes[plane_off[b]+c, y, x]]; first maximum wins and
+// NaN compares as the maximum (torch.argmax semantics).
+__global__ void par_labels_kernel(const float* __restrict__ planes, const int* __restrict__ plane_off,
+                                  const int64_t* __restrict__ key, int64_t* __restrict__ labels, int64_t hw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (i >= hw) return;
+    const int pbeg = plane_off[b], pend = plane_off[b + 1];
+    float best = planes[(int64_t)pbeg * hw + i];
+    int arg = pbeg;
+    for (int p = pbeg + 1; p < pend; ++p) {
+        const float v = planes[(int64_t)p * hw + i];
+        if (!(best != best) && (v > best || v != v)) { best = v; arg = p; }
+    }
+    labels[(int64_t)b * hw + i] = pend > pbeg ? key[arg] : 0;
+}
+
+static int make_geom(const int* dilations, int n_dil, float w1, float w2, ParGeom* g) {
+    XL_REQUIRE(n_dil >= 1 && n_dil <= XL_PAR_MAX_DIL, "PAR: n_dil=%d outside [1,%d]", n_dil, XL_PAR_MAX_DIL);
+    g->n_dil = n_dil;
+    const int K = 8 * n_dil;
+    float pos[8 * XL_PAR_MAX_DIL];
+    const float r2 = sqrtf(2.f);
+    for (int di = 0; di < n_dil; ++di) {
+        XL_REQUIRE(dilations[di] >= 1, "PAR: dilation %d < 1", dilations[di]);
+        g->dil[di] = dilations[di];
+        for (int t = 0; t < 8; ++t)
+            pos[di * 8 + t] = (float)dilations[di] * ((t == 0 || t == 2 || t == 5 || t == 7) ? r2 : 1.f);
+    }
+    // fp32 arithmetic in the reference's order (utils/PAR.py:74,84,86)
+    float mean = 0.f;
+    for (int k = 0; k < K; ++k) mean += pos[k];
+    mean /= K;
+    float var = 0.f;
+    for (int k = 0; k < K; ++k) var += (pos[k] - mean) * (pos[k] - mean);
+    const float sd = K > 1 ? sqrtf(var / (K - 1)) : NAN;
+    float mx = -INFINITY, e[8 * XL_PAR_MAX_DIL], sum = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float t = pos[k] / (sd + 1e-8f) / w1;
+        e[k] = -(t * t);
+        mx = fmaxf(mx, e[k]);
+    }
+    for (int k = 0; k < K; ++k) { e[k] = expf(e[k] - mx); sum += e[k]; }
+    for (int k = 0; k < K; ++k) g->pos[k] = w2 * (e[k] / sum);
+    return 0;
+}
+
+static int max_dilation(const ParGeom& g) {
+    int m = 0;
+    for (int i = 0; i < g.n_dil; ++i) m = g.dil[i] > m ? g.dil[i] : m;
+    return (m + 3) & ~3;  // halo: multiple of 4 floats so that every tile row stays 16 B-aligned
+}
+
+static size_t tile_smem_bytes(int halo, int planes) {
+    return (size_t)(kTX + 2 * halo) * (kTY + 2 * halo) * planes * sizeof(float);
+}
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t bytes, const char* what) {
+    XL_REQUIRE(bytes <= 227 * 1024, "%s: %zu B of shared memory (dilation too large for the tile)", what, bytes);
+    XL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+template <int NDIL>
+static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy, float* aff, int B, int H, int W,
+                           int Wp, const ParGeom& g, float w1, cudaStream_t st) {
+    const int halo = max_dilation(g);
+    const size_t smem = tile_smem_bytes(halo, 3);
+    if (int e = set_smem(par_affinity_kernel<NDIL>, smem, "par_affinity")) return e;
+    dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), B), block(32, 8);
+    par_affinity_kernel<NDIL><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
+    return check_launch("par_affinity_kernel");
+}
+
+template <int CCH>
+static int launch_iterate_c(const CUtensorMap& tm, const float* in, float* out, const int* plane_off, int img0, int nimg,
+                            int H, int W, const ParGeom& g, cudaStream_t st) {
+    const int halo = max_dilation(g);
+    const size_t smem = tile_smem_bytes(halo, CCH) + kStages * kG * kTY * kTX * sizeof(float) + 128;
+    if (int e = set_smem(par_iterate_kernel<CCH>, smem, "par_iterate")) return e;
+    dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), nimg);
+    par_iterate_kernel<CCH><<<grid, kParThreads, smem, st>>>(tm, in, out, plane_off, img0, H, W, halo, g);
+    return check_launch("par_iterate_kernel");
+}
+
+static int launch_iterate(const CUtensorMap& tm, const float* in, float* out, const int* plane_off, int img0, int nimg,
+                          int cch, int H, int W, const ParGeom& g, cudaStream_t st) {
+    switch (cch) {
+        case 1: return launch_iterate_c<1>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
+        case 2: return launch_iterate_c<2>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
+        default: return launch_iterate_c<3>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
+    }
+}
+
+#define XL_NDIL_SWITCH(n, CALL)                                                    \
+    switch (n) {                                                                   \
+        case 1: { constexpr int ND = 1; CALL; } break;                             \
+        case 2: { constexpr int ND = 2; CALL; } break;                             \
+        case 3: { constexpr int ND = 3; CALL; } break;                             \
+        case 4: { constexpr int ND = 4; CALL; } break;                             \
+        case 5: { constexpr int ND = 5; CALL; } break;                             \
+        case 6: { constexpr int ND = 6; CALL; } break;                             \
+        case 7: { constexpr int ND = 7; CALL; } break;                             \
+        default: { constexpr int ND = 8; CALL; } break;                            \
+    }
+
+}  // namespace xl
+
+using namespace xl;
+
+extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t stride_c, int64_t stride_y, int B,
+                                 int hi, int wi, int H, int W, const int* dilations, int n_dil, float w1, float w2,
+                                 int num_iter, int group, float* resize_ws, float* aff_ws, const float* planes_in,
+                                 float* planes_out, float* planes_tmp, const int* plane_off_dev, int max_c,
+                                 void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ParGeom g;
+    if (int e = make_geom(dilations, n_dil, w1, w2, &g)) return e;
+    XL_REQUIRE(B >= 0 && H > 0 && W > 0 && hi > 0 && wi > 0, "PAR: bad shape B=%d img=%dx%d out=%dx%d", B, hi, wi, H, W);
+    XL_REQUIRE(num_iter >= 0 && max_c >= 0, "PAR: num_iter=%d max_c=%d", num_iter, max_c);
+    if (B == 0) return 0;
+    if (group <= 0 || group > B) group = B;
+    XL_REQUIRE(group <= 65535, "PAR: launch group %d > 65535", group);
+    const bool iterate = planes_out != nullptr && num_iter > 0 && max_c > 0;
+    if (iterate) {
+        XL_REQUIRE(num_iter <= 1 || planes_tmp != nullptr, "PAR: num_iter=%d needs a ping-pong buffer", num_iter);
+        XL_REQUIRE(planes_in != planes_out && planes_tmp != planes_out && planes_in != planes_tmp,
+                   "PAR: in/out/tmp must not alias");
+    }
+    if (hi != H || wi != W) {
+        XL_REQUIRE(resize_ws != nullptr, "PAR: image %dx%d != mask %dx%d needs a resize workspace", hi, wi, H, W);
+        XL_REQUIRE(B * 3 <= 65535, "PAR: B too large for the resize launch");
+        dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * 3), block(32, 8);
+        par_resize_ac_kernel<<<grid, block, 0, st>>>(img, stride_b, stride_c, stride_y, resize_ws, hi, wi, H, W);
+        if (int e = check_launch("par_resize_ac_kernel")) return e;
+        img = resize_ws;
+        stride_y = W; stride_c = (int64_t)H * W; stride_b = 3 * stride_c;
+    }
+    const int cch = max_c < 3 ? max_c : 3;
+    const int Wp = (W + 3) & ~3;  // row pitch of the affinity workspace
+    CUtensorMap tm;
+    if (iterate) {
+        const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)group * 8 * n_dil};
+        const uint64_t strides[2] = {(uint64_t)Wp * 4, (uint64_t)Wp * H * 4};
+        const uint32_t box[3] = {kTX, kTY, kG};
+        if (int e = encode_tensor_map(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, aff_ws, dims, strides, box,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
+    for (int b0 = 0; b0 < B; b0 += group) {
+        const int nb = B - b0 < group ? B - b0 : group;
+        int e = 0;
+        XL_NDIL_SWITCH(n_dil, e = launch_affinity<ND>(img + (int64_t)b0 * stride_b, stride_b, stride_c, stride_y,
+                                                      aff_ws, nb, H, W, Wp, g, w1, st));
+        if (e) return e;
+        if (!iterate) {  // affinity only: aff_ws holds all B images
+            aff_ws += (int64_t)nb * 8 * n_dil * H * Wp;
+            continue;
+        }
+        const float* src = planes_in;
+        for (int it = 0; it < num_iter; ++it) {  // ping-pong so that the LAST step writes planes_out
+            float* dst = ((num_iter - 1 - it) & 1) ? planes_tmp : planes_out;
+            if ((e = launch_iterate(tm, src, dst, plane_off_dev, b0, nb, cch, H, W, g, st))) return e;
+            src = dst;
+        }
+    }
+    return 0;
+}
+
+extern "C" int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_t* plane_key_dev,
+                                int64_t* labels, int B, int H, int W, void* stream) {
+    XL_REQUIRE(B >= 0 && H > 0 && W > 0, "PAR labels: bad shape");
+    if (B == 0) return 0;
+    XL_REQUIRE(B <= 65535, "PAR labels: B=%d > 65535", B);
+    const int64_t hw = (int64_t)H * W;
+    dim3 grid((unsigned)ceil_div64(hw, 256), B);
+    par_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, plane_off_dev, plane_key_dev, labels, hw);
+    return check_launch("par_labels_kernel");
+}

@@ -1,0 +1,92 @@
+"""PAR -- drop-in for the reference's ``utils.PAR.PAR`` (utils/PAR.py:26-92) on sm_100a.
+
+Same constructor and ``forward(imgs, masks)`` signature; the arithmetic runs in
+``excel_par_forward`` (include/excel_b200.h).  ``refine_planes`` is the batched, ragged form used by
+the fused pipeline (per-image channel counts differ: background + present classes).
+"""
+import torch
+from torch import nn
+
+from . import _lib
+
+W1, W2 = 0.3, 0.01  # utils/PAR.py:36-37
+
+
+def _pitch(w):
+    return (w + 3) & ~3
+
+
+def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=1, w1=W1, w2=W2):
+    """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
+    Returns the refined planes [P,H,W] (a new tensor)."""
+    imgs = imgs.float()
+    if imgs.stride(-1) != 1:
+        imgs = imgs.contiguous()
+    planes = _lib.f32c(planes)
+    B, _, hi, wi = imgs.shape
+    P, H, W = planes.shape
+    if num_iter <= 0 or P == 0:
+        return planes.clone()
+    K = 8 * len(dilations)
+    g = B if group <= 0 else min(group, B)
+    dev = planes.device
+    aff = torch.empty((g, K, H, _pitch(W)), dtype=torch.float32, device=dev)   # internal layout: row pitch % 4 == 0
+    rs = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
+    out = torch.empty_like(planes)
+    tmp = torch.empty_like(planes) if num_iter > 1 else None
+    _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
+              _lib.int_array(dilations), len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
+              _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off), int(max_c), _lib.stream())
+    return out
+
+
+def par_affinity(imgs, size, dilations, w1=W1, w2=W2):
+    """utils/PAR.py:67-86 only: imgs [B,3,hi,wi] -> aff [B,8*n_dil,H,W]."""
+    imgs = imgs.float()
+    if imgs.stride(-1) != 1:
+        imgs = imgs.contiguous()
+    B, _, hi, wi = imgs.shape
+    H, W = size
+    aff = torch.empty((B, 8 * len(dilations), H, _pitch(W)), dtype=torch.float32, device=imgs.device)
+    rs = torch.empty((B, 3, H, W), dtype=torch.float32, device=imgs.device) if (hi, wi) != (H, W) else None
+    _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
+              _lib.int_array(dilations), len(dilations), w1, w2, 0, B, _lib.ptr(rs), _lib.ptr(aff),
+              None, None, None, None, 0, _lib.stream())
+    return aff[..., :W]
+
+
+def par_labels(planes, plane_off, plane_key, B):
+    """utils/affutils.py:86-87: labels [B,H,W] int64 = plane_key[argmax over image b's planes]."""
+    P, H, W = planes.shape
+    labels = torch.empty((B, H, W), dtype=torch.int64, device=planes.device)
+    _lib.call("excel_par_labels", _lib.ptr(planes), _lib.ptr(plane_off), _lib.ptr(plane_key), _lib.ptr(labels),
+              B, H, W, _lib.stream())
+    return labels
+
+
+class PAR(nn.Module):
+    """Same interface as utils/PAR.py:26 -- ``PAR(dilations, num_iter)(imgs, masks)``."""
+
+    def __init__(self, dilations, num_iter, group=1):
+        super().__init__()
+        self.dilations = list(dilations)
+        self.num_iter = num_iter
+        self.group = group          # images per launch group (L2 residency of the affinity planes)
+        self.dim = 2
+        self.w1 = W1
+        self.w2 = W2
+        # kept for state_dict compatibility with the reference module (utils/PAR.py:31-32)
+        kernel = torch.zeros(8, 1, 3, 3)
+        for i, (r, c) in enumerate(((0, 0), (0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1), (2, 2))):
+            kernel[i, 0, r, c] = 1
+        self.register_buffer("kernel", kernel)
+
+    @torch.no_grad()
+    def forward(self, imgs, masks):
+        b, c, h, w = masks.shape
+        if imgs.shape[0] != b:
+            raise RuntimeError(f"PAR: batch mismatch imgs {tuple(imgs.shape)} vs masks {tuple(masks.shape)}")
+        off = torch.arange(0, (b + 1) * c, c, dtype=torch.int32, device=masks.device)
+        out = par_refine_planes(imgs, masks.reshape(b * c, h, w), off, c, self.dilations, self.num_iter,
+                                self.group, self.w1, self.w2)
+        return out.view(b, c, h, w)
