@@ -170,55 +170,74 @@ constexpr int kG = 2;        // taps per TMA stage (8 KB)
 constexpr int kStages = 4;   // ring depth: kStages-1 stages (24 KB per CTA, 48 KB per SM) in flight
 constexpr int kParThreads = 256 + 32;  // 8 consumer warps + 1 TMA producer warp
 
+// shared-memory loads on 32-bit shared addresses (keeps the address arithmetic 32-bit; `volatile` pins
+// them behind the mbarrier waits)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
 template <int O>
-__device__ __forceinline__ void load4_shift(const float* p, float (&m)[4]) {
-    // m[i] = p[i + O] for a 16 B-aligned p
+__device__ __forceinline__ void load4_shift(uint32_t p, float (&m)[4]) {
+    // m[i] = smem_float[p/4 + i + O] for a 16 B-aligned byte address p
     if constexpr (O == 0) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
+        const float4 v = lds128(p);
         m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
     } else if constexpr (O == -1) {
-        const float l = p[-1];
-        const float4 v = *reinterpret_cast<const float4*>(p);
+        const float l = lds32(p - 4);
+        const float4 v = lds128(p);
         m[0] = l; m[1] = v.x; m[2] = v.y; m[3] = v.z;
     } else if constexpr (O == 1) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        const float r = p[4];
+        const float4 v = lds128(p);
+        const float r = lds32(p + 16);
         m[0] = v.y; m[1] = v.z; m[2] = v.w; m[3] = r;
     } else if constexpr (O == -2) {
-        const float2 l = *reinterpret_cast<const float2*>(p - 2);
-        const float2 v = *reinterpret_cast<const float2*>(p);
+        const float2 l = lds64(p - 8);
+        const float2 v = lds64(p);
         m[0] = l.x; m[1] = l.y; m[2] = v.x; m[3] = v.y;
     } else {  // O == 2
-        const float2 v = *reinterpret_cast<const float2*>(p + 2);
-        const float2 r = *reinterpret_cast<const float2*>(p + 4);
+        const float2 v = lds64(p + 8);
+        const float2 r = lds64(p + 16);
         m[0] = v.x; m[1] = v.y; m[2] = r.x; m[3] = r.y;
     }
 }
 
-// MODE: 1 / 2 = dilation 1 / 2 (compile-time shifts); 0 = dilation % 4 == 0 (aligned LDS.128); -1 = any
+// kG taps T0..T0+kG-1 of one dilation.  MODE: 1 / 2 = dilation 1 / 2 (compile-time shifts);
+// 0 = dilation % 4 == 0 (aligned LDS.128); -1 = any dilation (scalar loads).
+// as: byte address of this thread's affinities in the stage; ctr[c]: byte address of its centre pixel in
+// plane c; d4 / dW4: byte offsets of one dilation step in x / y.
 template <int CCH, int MODE, int T0>
-__device__ __forceinline__ void par_taps(const float* __restrict__ as, const float* __restrict__ ctr, int cs, int d, int dW,
-                                         float (&acc)[4][CCH]) {
+__device__ __forceinline__ void par_taps(uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float (&acc)[4][CCH]) {
 #pragma unroll
     for (int tt = 0; tt < kG; ++tt) {
-        constexpr int dummy = 0; (void)dummy;
         const int t = T0 + tt;
-        const float4 a4 = *reinterpret_cast<const float4*>(as + tt * kTY * kTX);
+        const float4 a4 = lds128(as + tt * kTY * kTX * 4);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const int dy = tap_dy(t), dx = tap_dx(t);
 #pragma unroll
         for (int c = 0; c < CCH; ++c) {
             float m[4];
+            const uint32_t row = ctr[c] + dy * dW4;
             if constexpr (MODE == 1 || MODE == 2) {
-                const float* p = ctr + c * cs + dy * dW;
-                if (dx < 0) load4_shift<-MODE>(p, m);
-                else if (dx > 0) load4_shift<MODE>(p, m);
-                else load4_shift<0>(p, m);
+                if (dx < 0) load4_shift<-MODE>(row, m);
+                else if (dx > 0) load4_shift<MODE>(row, m);
+                else load4_shift<0>(row, m);
             } else if constexpr (MODE == 0) {
-                load4_shift<0>(ctr + c * cs + dy * dW + dx * d, m);
+                load4_shift<0>(row + dx * d4, m);
             } else {
-                const float* p = ctr + c * cs + dy * dW + dx * d;
-                m[0] = p[0]; m[1] = p[1]; m[2] = p[2]; m[3] = p[3];
+                const uint32_t p = row + dx * d4;
+                m[0] = lds32(p); m[1] = lds32(p + 4); m[2] = lds32(p + 8); m[3] = lds32(p + 12);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(a[i], m[i], acc[i][c]);
@@ -227,22 +246,53 @@ __device__ __forceinline__ void par_taps(const float* __restrict__ as, const flo
 }
 
 template <int CCH, int T0>
-__device__ __forceinline__ void par_taps_mode(int mode, const float* as, const float* ctr, int cs, int d, int dW,
+__device__ __forceinline__ void par_taps_mode(int mode, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4,
                                               float (&acc)[4][CCH]) {
-    if (mode == 0) par_taps<CCH, 0, T0>(as, ctr, cs, d, dW, acc);
-    else if (mode == 1) par_taps<CCH, 1, T0>(as, ctr, cs, d, dW, acc);
-    else if (mode == 2) par_taps<CCH, 2, T0>(as, ctr, cs, d, dW, acc);
-    else par_taps<CCH, -1, T0>(as, ctr, cs, d, dW, acc);
+    if (mode == 0) par_taps<CCH, 0, T0>(as, ctr, d4, dW4, acc);
+    else if (mode == 1) par_taps<CCH, 1, T0>(as, ctr, d4, dW4, acc);
+    else if (mode == 2) par_taps<CCH, 2, T0>(as, ctr, d4, dW4, acc);
+    else par_taps<CCH, -1, T0>(as, ctr, d4, dW4, acc);
+}
+
+// Replicate padding for a tile that TMA zero-filled outside the image: copy the nearest in-image
+// column, then the nearest in-image row, inside shared memory.  Called by the 256 consumer threads.
+__device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, int TW, int TH, int H, int W, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int c_lo = max(0, -xl), c_hi = min(TW, W - xl) - 1;
+    const int r_lo = max(0, -yl), r_hi = min(TH, H - yl) - 1;
+    if (c_lo > 0 || c_hi < TW - 1) {
+        for (int q = warp; q < np * TH; q += 8) {
+            const int r = q % TH;
+            if (r < r_lo || r > r_hi) continue;
+            float* row = sm + q * TW;
+            const float vl = row[c_lo], vr = row[c_hi];
+            for (int c = lane; c < c_lo; c += 32) row[c] = vl;
+            for (int c = c_hi + 1 + lane; c < TW; c += 32) row[c] = vr;
+        }
+    }
+    bar_sync(1, 256);
+    if (r_lo > 0 || r_hi < TH - 1) {
+        for (int q = warp; q < np * TH; q += 8) {
+            const int r = q % TH;
+            if (r >= r_lo && r <= r_hi) continue;
+            const float* srow = sm + (q - r + (r < r_lo ? r_lo : r_hi)) * TW;
+            float* row = sm + q * TW;
+            for (int c = lane; c < TW; c += 32) row[c] = srow[c];
+        }
+    }
+    bar_sync(1, 256);
 }
 
 template <int CCH>
 __global__ void __launch_bounds__(kParThreads, 2)
-par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __restrict__ in, float* __restrict__ out,
-                   const int* __restrict__ plane_off, int img0, int H, int W, int halo, ParGeom g) {
+par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_constant__ CUtensorMap tm_in, int tma_in,
+                   const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ plane_off, int img0,
+                   int H, int W, int halo, ParGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages];
+    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tile_full, tile_empty;
     // [kStages][kG][kTY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
-    float* ring = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    // (offset arithmetic, not an integer round trip, so the compiler keeps the shared address space)
+    float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     float* sm = ring + kStages * kG * kTY * kTX;
     const int TW = kTX + 2 * halo, TH = kTY + 2 * halo, cs = TH * TW;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = img0 + blockIdx.z;
@@ -251,7 +301,6 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __re
     const int64_t plane = (int64_t)H * W;
     const int pbeg = plane_off[b], pend = plane_off[b + 1];
     const int npass = (pend - pbeg + CCH - 1) / CCH;
-    const int total = npass * nchunk;
     constexpr uint32_t kStageBytes = kG * kTY * kTX * sizeof(float);
 
     if (tid == 0) {
@@ -259,18 +308,27 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __re
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 8);
         }
+        mbar_init(&tile_full, 1);
+        mbar_init(&tile_empty, 8);
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (tid >= 256) {  // ---- producer warp: one lane streams the affinity chunks through the ring
+    if (tid >= 256) {  // ---- producer warp: one lane drives TMA
         if (tid == 256) {
-            for (int i = 0; i < total; ++i) {
-                const int s = i % kStages;
-                if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
-                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                tma_load_3d(ring + s * kG * kTY * kTX, &tm_aff, &full_bar[s], x0, y0,
-                            (int)blockIdx.z * K + (i % nchunk) * kG);
+            int i = 0;
+            for (int pass = 0; pass < npass; ++pass) {
+                if (tma_in) {  // mask tile (+halo) of this pass; zero-filled outside the image
+                    if (pass > 0) mbar_wait(&tile_empty, (pass - 1) & 1);
+                    mbar_arrive_expect_tx(&tile_full, (uint32_t)(CCH * cs * sizeof(float)));
+                    tma_load_3d(sm, &tm_in, &tile_full, x0 - halo, y0 - halo, pbeg + pass * CCH);
+                }
+                for (int ch = 0; ch < nchunk; ++ch, ++i) {  // affinity chunks through the ring
+                    const int s = i % kStages;
+                    if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
+                    mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                    tma_load_3d(ring + s * kG * kTY * kTX, &tm_aff, &full_bar[s], x0, y0, (int)blockIdx.z * K + ch * kG);
+                }
             }
         }
         return;
@@ -278,15 +336,24 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __re
 
     // ---- consumers: thread (tx4, ty) owns pixels (y0+ty, x0+4*tx4 .. +3)
     const int tx4 = tid & 7, ty = tid >> 3;
-    const float* ctr = sm + (ty + halo) * TW + 4 * tx4 + halo;
-    const float* as0 = ring + ty * kTX + 4 * tx4;
+    const bool border = x0 - halo < 0 || y0 - halo < 0 || x0 + kTX + halo > W || y0 + kTY + halo > H;
+    uint32_t ctr[CCH];
+#pragma unroll
+    for (int c = 0; c < CCH; ++c) ctr[c] = smem_u32(sm + c * cs + (ty + halo) * TW + 4 * tx4 + halo);
+    const uint32_t as0 = smem_u32(ring + ty * kTX + 4 * tx4);
     int it = 0;
-    for (int pc = pbeg; pc < pend; pc += CCH) {
+    for (int pass = 0; pass < npass; ++pass) {
+        const int pc = pbeg + pass * CCH;
         const int np = min(CCH, pend - pc);
-        if (pc != pbeg) bar_sync(1, 256);
-        stage_tile_async(sm, in + (int64_t)pc * plane, plane, W, np, x0, y0, halo, TW, TH, H, W, tid);
-        cp_async_wait_all();
-        bar_sync(1, 256);
+        if (tma_in) {
+            mbar_wait(&tile_full, pass & 1);
+            if (border) fix_border(sm, CCH, x0 - halo, y0 - halo, TW, TH, H, W, tid);
+        } else {
+            if (pass > 0) bar_sync(1, 256);
+            stage_tile_async(sm, in + (int64_t)pc * plane, plane, W, np, x0, y0, halo, TW, TH, H, W, tid);
+            cp_async_wait_all();
+            bar_sync(1, 256);
+        }
         float acc[4][CCH];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -294,21 +361,27 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const float* __re
             for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
 #pragma unroll 1
         for (int di = 0; di < g.n_dil; ++di) {
-            const int d = g.dil[di], dW = d * TW;
+            const int d = g.dil[di];
+            const int d4 = d * 4, dW4 = d * TW * 4;
             const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
 #pragma unroll
             for (int q = 0; q < 8 / kG; ++q) {
                 const int s = it % kStages;
                 mbar_wait(&full_bar[s], (it / kStages) & 1);
-                const float* as = as0 + s * kG * kTY * kTX;
-                if (q == 0) par_taps_mode<CCH, 0 * kG>(mode, as, ctr, cs, d, dW, acc);
-                else if (q == 1) par_taps_mode<CCH, 1 * kG>(mode, as, ctr, cs, d, dW, acc);
-                else if (q == 2) par_taps_mode<CCH, 2 * kG>(mode, as, ctr, cs, d, dW, acc);
-                else par_taps_mode<CCH, 3 * kG>(mode, as, ctr, cs, d, dW, acc);
+                const uint32_t as = as0 + s * kStageBytes;
+                if (q == 0) par_taps_mode<CCH, 0 * kG>(mode, as, ctr, d4, dW4, acc);
+                else if (q == 1) par_taps_mode<CCH, 1 * kG>(mode, as, ctr, d4, dW4, acc);
+                else if (q == 2) par_taps_mode<CCH, 2 * kG>(mode, as, ctr, d4, dW4, acc);
+                else par_taps_mode<CCH, 3 * kG>(mode, as, ctr, d4, dW4, acc);
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with stage s
                 ++it;
             }
+        }
+        if (tma_in && pass + 1 < npass) {  // hand the mask tile back to the producer
+            if (border) fence_proxy_async_smem();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&tile_empty);
         }
         const int y = y0 + ty, x = x0 + 4 * tx4;
         if (y < H) {
@@ -405,22 +478,24 @@ static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy,
 }
 
 template <int CCH>
-static int launch_iterate_c(const CUtensorMap& tm, const float* in, float* out, const int* plane_off, int img0, int nimg,
-                            int H, int W, const ParGeom& g, cudaStream_t st) {
+static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, const float* in, float* out,
+                            const int* plane_off, int img0, int nimg, int H, int W, const ParGeom& g, cudaStream_t st) {
     const int halo = max_dilation(g);
     const size_t smem = tile_smem_bytes(halo, CCH) + kStages * kG * kTY * kTX * sizeof(float) + 128;
     if (int e = set_smem(par_iterate_kernel<CCH>, smem, "par_iterate")) return e;
     dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), nimg);
-    par_iterate_kernel<CCH><<<grid, kParThreads, smem, st>>>(tm, in, out, plane_off, img0, H, W, halo, g);
+    par_iterate_kernel<CCH><<<grid, kParThreads, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out, plane_off,
+                                                             img0, H, W, halo, g);
     return check_launch("par_iterate_kernel");
 }
 
-static int launch_iterate(const CUtensorMap& tm, const float* in, float* out, const int* plane_off, int img0, int nimg,
-                          int cch, int H, int W, const ParGeom& g, cudaStream_t st) {
+static int launch_iterate(const CUtensorMap& tm, const CUtensorMap* tm_in, const float* in, float* out,
+                          const int* plane_off, int img0, int nimg, int cch, int H, int W, const ParGeom& g,
+                          cudaStream_t st) {
     switch (cch) {
-        case 1: return launch_iterate_c<1>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
-        case 2: return launch_iterate_c<2>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
-        default: return launch_iterate_c<3>(tm, in, out, plane_off, img0, nimg, H, W, g, st);
+        case 1: return launch_iterate_c<1>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
+        case 2: return launch_iterate_c<2>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
+        default: return launch_iterate_c<3>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
     }
 }
 
@@ -443,8 +518,8 @@ using namespace xl;
 extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t stride_c, int64_t stride_y, int B,
                                  int hi, int wi, int H, int W, const int* dilations, int n_dil, float w1, float w2,
                                  int num_iter, int group, float* resize_ws, float* aff_ws, const float* planes_in,
-                                 float* planes_out, float* planes_tmp, const int* plane_off_dev, int max_c,
-                                 void* stream) {
+                                 float* planes_out, float* planes_tmp, const int* plane_off_dev, int total_planes,
+                                 int max_c, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ParGeom g;
     if (int e = make_geom(dilations, n_dil, w1, w2, &g)) return e;
@@ -478,6 +553,23 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         if (int e = encode_tensor_map(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, aff_ws, dims, strides, box,
                                       CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     }
+    // mask tiles (+halo) also move by TMA when the planes satisfy its alignment rules (else cp.async):
+    // one map per ping-pong buffer
+    const float* bufs[3] = {planes_in, planes_out, planes_tmp};
+    CUtensorMap tm_planes[3];
+    bool tma_planes = iterate && (W % 4) == 0 && total_planes > 0;
+    for (int i = 0; i < 3 && tma_planes; ++i)
+        if (bufs[i] && (reinterpret_cast<uintptr_t>(bufs[i]) & 15)) tma_planes = false;
+    if (tma_planes) {
+        const int halo = max_dilation(g);
+        const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)total_planes};
+        const uint64_t strides[2] = {(uint64_t)W * 4, (uint64_t)W * H * 4};
+        const uint32_t box[3] = {(uint32_t)(kTX + 2 * halo), (uint32_t)(kTY + 2 * halo), (uint32_t)cch};
+        for (int i = 0; i < 3; ++i)
+            if (bufs[i])
+                if (int e = encode_tensor_map(&tm_planes[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bufs[i], dims, strides, box,
+                                              CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    }
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = B - b0 < group ? B - b0 : group;
         int e = 0;
@@ -491,7 +583,9 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         const float* src = planes_in;
         for (int it = 0; it < num_iter; ++it) {  // ping-pong so that the LAST step writes planes_out
             float* dst = ((num_iter - 1 - it) & 1) ? planes_tmp : planes_out;
-            if ((e = launch_iterate(tm, src, dst, plane_off_dev, b0, nb, cch, H, W, g, st))) return e;
+            const CUtensorMap* tmi = !tma_planes ? nullptr
+                                     : &tm_planes[src == planes_in ? 0 : (src == planes_out ? 1 : 2)];
+            if ((e = launch_iterate(tm, tmi, src, dst, plane_off_dev, b0, nb, cch, H, W, g, st))) return e;
             src = dst;
         }
     }

@@ -16,7 +16,7 @@ def _pitch(w):
     return (w + 3) & ~3
 
 
-def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=1, w1=W1, w2=W2):
+def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2):
     """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
     Returns the refined planes [P,H,W] (a new tensor)."""
     imgs = imgs.float()
@@ -36,7 +36,7 @@ def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group
     tmp = torch.empty_like(planes) if num_iter > 1 else None
     _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
               _lib.int_array(dilations), len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
-              _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off), int(max_c), _lib.stream())
+              _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off), P, int(max_c), _lib.stream())
     return out
 
 
@@ -51,7 +51,7 @@ def par_affinity(imgs, size, dilations, w1=W1, w2=W2):
     rs = torch.empty((B, 3, H, W), dtype=torch.float32, device=imgs.device) if (hi, wi) != (H, W) else None
     _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
               _lib.int_array(dilations), len(dilations), w1, w2, 0, B, _lib.ptr(rs), _lib.ptr(aff),
-              None, None, None, None, 0, _lib.stream())
+              None, None, None, None, 0, 0, _lib.stream())
     return aff[..., :W]
 
 
@@ -67,7 +67,7 @@ def par_labels(planes, plane_off, plane_key, B):
 class PAR(nn.Module):
     """Same interface as utils/PAR.py:26 -- ``PAR(dilations, num_iter)(imgs, masks)``."""
 
-    def __init__(self, dilations, num_iter, group=1):
+    def __init__(self, dilations, num_iter, group=0):
         super().__init__()
         self.dilations = list(dilations)
         self.num_iter = num_iter

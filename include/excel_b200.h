@@ -35,7 +35,7 @@ int excel_device_arch(int device);    /* 10*major + minor of `device` (100 on B2
  *     aff_k = softmax_k(-mean_c((|I_k-I_0|/(std_c+1e-8)/w1)^2)) + w2*softmax_k(-(pos_k/(std(pos)+1e-8)/w1)^2),
  *     neighbour k = dilation-major, taps in the order of get_kernel (:10-24), replicate padding.
  *   Propagation (:88-90): num_iter steps over the packed mask planes [P,H,W]; plane_off_dev [B+1]
- *     (int32, device) gives image b's planes, max_c = max planes of one image.  The result lands in
+ *     (int32, device) gives image b's planes, total_planes = P, max_c = max planes of one image.  The result lands in
  *     planes_out; planes_tmp [P,H,W] is the ping-pong buffer (needed when num_iter > 1).
  *   Images are processed in launch groups of `group` (<=0: all B): affinity of the group, then all
  *   its steps, so aff_ws only needs [group,K,H,Wp] floats, Wp = round_up(W,4) (internal layout: the
@@ -45,7 +45,8 @@ int excel_device_arch(int device);    /* 10*major + minor of `device` (100 on B2
 int excel_par_forward(const float* img, int64_t stride_b, int64_t stride_c, int64_t stride_y, int B,
                       int hi, int wi, int H, int W, const int* dilations_host, int n_dil, float w1, float w2,
                       int num_iter, int group, float* resize_ws, float* aff_ws, const float* planes_in,
-                      float* planes_out, float* planes_tmp, const int* plane_off_dev, int max_c, void* stream);
+                      float* planes_out, float* planes_tmp, const int* plane_off_dev, int total_planes, int max_c,
+                      void* stream);
 
 /* utils/affutils.py:86-87 (_refine_cams): labels[b] = plane_key[argmax_c planes of image b]
  * (first maximum wins, NaN is a maximum); labels [B,H,W] int64, plane_key_dev [P] int64. */
