@@ -21,6 +21,15 @@ SIGNATURES = {
     "excel_device_arch": ([_i], _i),
     "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "excel_svc_mean_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),
+    "excel_svc_sinkhorn": ([_p, _i, _i, _i, _p, _p, _p], _i),
+    "excel_svc_build_trans": ([_p, _p, _p, _i, _i, _p, _p], _i),
+    "excel_svc_box_mask": ([_p, _i64, _i64, _p, _p, _i, _i, _i, _c.c_double, _p, _p, _p], _i),
+    "excel_svc_propagate": ([_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p], _i),
+    "excel_svc_cams_to_planes": ([_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p], _i),
+    "excel_token_normalize": ([_p, _i, _i, _i, _p, _p, _p], _i),
+    "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _p, _p], _i),
+    "excel_sgemm": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _i64, _i64, _i64, _f, _i, _i, _p], _i),
 }
 
 _lib = None

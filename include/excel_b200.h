@@ -53,6 +53,63 @@ int excel_par_forward(const float* img, int64_t stride_b, int64_t stride_c, int6
 int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_t* plane_key_dev,
                      int64_t* labels, int B, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- SVC (utils/affutils.py) ------ */
+
+/* utils/affutils.py:180,197 (training-free branch of refine_cams_with_aff): A[b] = mean over the last
+ * `attn_layers` of attn[l, b, 1:, 1:].  attn [L,B,N,N] with element strides (stride_l, stride_b, N, 1);
+ * A [B, N-1, N-1]. */
+int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N,
+                             int attn_layers, float* A, void* stream);
+
+/* utils/affutils.py:11-16 (compute_trans_mat, the 1 + 2 rounds of column / row normalisation) in scaling
+ * form: trans = diag(r) A diag(c).  A [B,np,np]; r, c [B,np] outputs. rounds = 3 in the reference. */
+int excel_svc_sinkhorn(const float* A, int B, int np, int rounds, float* r, float* c, void* stream);
+
+/* utils/affutils.py:17: T = (S + S^T)/2 with S = diag(r) A diag(c), materialised [B,np,np] (only the
+ * standalone compute_trans_mat API needs it; the squaring of :20 is then excel_sgemm). */
+int excel_svc_build_trans(const float* A, const float* r, const float* c, int B, int np, float* T, void* stream);
+
+/* utils/affutils.py:26-53 (scoremap2bbox, multi_contour_eval=True) + :207-215 for Q (image, class) pairs:
+ * cam = attr[img_of[q], :, cls_of[q]] viewed gh x gw (element strides attr_stride_b, attr_stride_p, 1);
+ * uint8(cam*255) truncation, thr = int(caa_thre*max), strict >, union of the clipped bounding boxes of the
+ * 8-connected components (== cv2.findContours + boundingRect).  v[q] = mask * cam [Q, gh*gw];
+ * mask_out [Q, gh*gw] optional (NULL to skip). */
+int excel_svc_box_mask(const float* attr, int64_t attr_stride_b, int64_t attr_stride_p, const int* img_of_dev,
+                       const int* cls_of_dev, int Q, int gh, int gw, double caa_thre, float* v, float* mask_out,
+                       void* stream);
+
+/* utils/affutils.py:17,20 + :215-221: out[q] = T^hops v[q] with T = (S + S^T)/2, S = diag(r) A diag(c)
+ * of image img_of[q]; hops = 2 reproduces ((T@T) * mask) @ cam without forming T@T.  tmp1, tmp2 [Q,np]. */
+int excel_svc_propagate(const float* A, const float* r, const float* c, const int* img_of_dev, const float* v, int Q,
+                        int np, int hops, float* tmp1, float* tmp2, float* out, void* stream);
+
+/* utils/affutils.py:55-78 (generate_cam_label / scale_cam_image) + :165-166: per class min-max with
+ * (1e-7 + max), bilinear resize gh x gw -> H x W with cv2.resize semantics, background plane
+ * 1 - max_c; writes the packed PAR planes [P,H,W] (plane_off_dev[b] = background of image b, then its
+ * classes; class slot of image b starts at plane_off[b] - b).  minmax_ws [2*Q] floats. */
+int excel_svc_cams_to_planes(const float* refined, int Q, int gh, int gw, const int* plane_off_dev, int B, int H,
+                             int W, float* minmax_ws, float* planes, void* stream);
+
+/* ---------------------------------------------------------------- CAM (clip/clip.py) ---------- */
+
+/* clip/clip.py:353 (generate_clip_fts): out = tok / ||tok||_2 over the TOKEN axis, per (b, channel).
+ * tok, out [B,N,E]; norm_ws [B,E]. */
+int excel_token_normalize(const float* tok, int B, int N, int E, float* norm_ws, float* out, void* stream);
+
+/* clip/clip.py:288-310 (clip_feature_surgery, redundant_feats=None): feats [B,N,E], text [T,E] ->
+ * out [B,N,T], min-max normalised over all N tokens per (b,t), no epsilon.  S_ws [B,N,T]. */
+int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, float* S_ws, float* out,
+                      void* stream);
+
+/* ---------------------------------------------------------------- dense fp32 GEMM ------------- */
+
+/* C[b] = act(alpha * A[b] * op(B[b]) + bias) + residual[b]; exact fp32 (SIMT).  A [M,K] (lda); B [N,K] (ldb)
+ * if b_is_nk (nn.Linear weight layout) else [K,N]; C, residual [M,N] (ldc); act: 0 none, 1 QuickGELU
+ * (clip/clip_surgery_model.py:280-282). */
+int excel_sgemm(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
+                int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB, int64_t strideC,
+                float alpha, int b_is_nk, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
