@@ -27,6 +27,11 @@ int check_launch(const char* what);  // cudaGetLastError() -> 0 / error code (me
         }                                                                                    \
     } while (0)
 
+// fp32 SIMT GEMM with a two-level batch (gemm_simt.cu)
+int sgemm2(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
+           int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t sA, int64_t sB, int64_t sC, int nb2, int64_t sA2,
+           int64_t sB2, int64_t sC2, float alpha, int b_is_nk, int act, cudaStream_t st);
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

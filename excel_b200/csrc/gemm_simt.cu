@@ -16,14 +16,15 @@ template <bool B_NK>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C,
              const float* __restrict__ bias, const float* __restrict__ residual, int M, int N, int K, int64_t lda,
-             int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, float alpha, int act) {
+             int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, int nb2, int64_t sA2, int64_t sB2,
+             int64_t sC2, float alpha, int act) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
-    const int bz = blockIdx.z;
-    A += (int64_t)bz * sA;
-    Bm += (int64_t)bz * sB;
-    C += (int64_t)bz * sC;
-    if (residual) residual += (int64_t)bz * sC;
+    const int bz = blockIdx.z / nb2, b2 = blockIdx.z % nb2;  // two-level batch (image, head)
+    A += (int64_t)bz * sA + (int64_t)b2 * sA2;
+    Bm += (int64_t)bz * sB + (int64_t)b2 * sB2;
+    C += (int64_t)bz * sC + (int64_t)b2 * sC2;
+    if (residual) residual += (int64_t)bz * sC + (int64_t)b2 * sC2;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
     float acc[4][4] = {};
@@ -86,18 +87,27 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
 
 using namespace xl;
 
+namespace xl {
+int sgemm2(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
+           int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t sA, int64_t sB, int64_t sC, int nb2, int64_t sA2,
+           int64_t sB2, int64_t sC2, float alpha, int b_is_nk, int act, cudaStream_t st) {
+    XL_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0 && nb2 >= 1, "sgemm: bad dimension");
+    if (M == 0 || N == 0 || batch == 0) return 0;
+    XL_REQUIRE((int64_t)batch * nb2 <= 65535 && ceil_div(M, BM) <= 65535, "sgemm: grid too large");
+    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch * nb2);
+    if (b_is_nk)
+        sgemm_kernel<true><<<grid, 256, 0, st>>>(A, B, C, bias, residual, M, N, K, lda, ldb, ldc, sA, sB, sC, nb2, sA2, sB2,
+                                                 sC2, alpha, act);
+    else
+        sgemm_kernel<false><<<grid, 256, 0, st>>>(A, B, C, bias, residual, M, N, K, lda, ldb, ldc, sA, sB, sC, nb2, sA2, sB2,
+                                                  sC2, alpha, act);
+    return check_launch("sgemm_kernel");
+}
+}  // namespace xl
+
 extern "C" int excel_sgemm(const float* A, const float* B, float* C, const float* bias, const float* residual, int M,
                            int N, int K, int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA,
                            int64_t strideB, int64_t strideC, float alpha, int b_is_nk, int act, void* stream) {
-    XL_REQUIRE(M >= 0 && N >= 0 && K >= 0 && batch >= 0, "sgemm: negative dimension");
-    if (M == 0 || N == 0 || batch == 0) return 0;
-    XL_REQUIRE(batch <= 65535 && ceil_div(M, BM) <= 65535, "sgemm: grid too large");
-    dim3 grid(ceil_div(N, BN), ceil_div(M, BM), batch);
-    if (b_is_nk)
-        sgemm_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, residual, M, N, K, lda, ldb, ldc, strideA,
-                                                                   strideB, strideC, alpha, act);
-    else
-        sgemm_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(A, B, C, bias, residual, M, N, K, lda, ldb, ldc, strideA,
-                                                                    strideB, strideC, alpha, act);
-    return check_launch("sgemm_kernel");
+    return xl::sgemm2(A, B, C, bias, residual, M, N, K, lda, ldb, ldc, batch, strideA, strideB, strideC, 1, 0, 0, 0, alpha,
+                      b_is_nk, act, (cudaStream_t)stream);
 }

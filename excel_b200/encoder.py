@@ -1,0 +1,121 @@
+"""CLIP-surgery vision encoder on sm_100a -- the engine behind ``clip.generate_clip_fts``
+(clip/clip.py:348-358; VisionTransformer.forward, clip/clip_surgery_model.py:418-448).
+
+``SurgeryViT`` owns a device copy of the frozen encoder weights (a plain dict of fp32 tensors) and calls
+``excel_vit_forward``; ``from_visual`` builds it from a reference / OpenAI-CLIP style ``VisionTransformer``
+module, so the reference's ``ExCEL_model.encoder`` can be used as is.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .clip import token_normalize
+
+_BLOCK_FIELDS = (("ln1_w", "ln_1.weight"), ("ln1_b", "ln_1.bias"), ("in_w", "in_proj_weight"), ("in_b", "in_proj_bias"),
+                 ("out_w", "out_proj.weight"), ("out_b", "out_proj.bias"), ("ln2_w", "ln_2.weight"), ("ln2_b", "ln_2.bias"),
+                 ("fc_w", "c_fc.weight"), ("fc_b", "c_fc.bias"), ("proj_w", "c_proj.weight"), ("proj_b", "c_proj.bias"))
+
+
+def pack_from_visual(visual):
+    """state_dict of a VisionTransformer (clip/clip_surgery_model.py:374) -> flat weight pack.  Works before
+    or after ``reload_self_attn`` (the surgery ``Attention`` keeps clones of in_proj / out_proj, :396-405)."""
+    sd = {k: v.detach() for k, v in visual.state_dict().items()}
+    W = {k: sd[k] for k in ("conv1.weight", "class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias",
+                            "ln_post.weight", "ln_post.bias", "proj")}
+    L = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
+    for i in range(L):
+        p, o = "transformer.resblocks.%d." % i, "blocks.%d." % i
+        if p + "attn.in_proj_weight" in sd:
+            names = ("attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight", "attn.out_proj.bias")
+        else:
+            names = ("attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias")
+        for dst, src in zip(("in_proj_weight", "in_proj_bias", "out_proj.weight", "out_proj.bias"), names):
+            W[o + dst] = sd[p + src]
+        for n in ("ln_1.weight", "ln_1.bias", "ln_2.weight", "ln_2.bias"):
+            W[o + n] = sd[p + n]
+        for n in ("c_fc.weight", "c_fc.bias", "c_proj.weight", "c_proj.bias"):
+            W[o + n] = sd[p + "mlp." + n]
+    heads = getattr(visual, "num_heads", None) or sd["conv1.weight"].shape[0] // 64
+    W["meta"] = torch.tensor([L, heads, sd["conv1.weight"].shape[-1]], dtype=torch.int64)
+    return W
+
+
+class SurgeryViT:
+    """Frozen CLIP-surgery ViT.  ``weights``: pack as produced by ``pack_from_visual`` (any device)."""
+
+    def __init__(self, weights, n_surgery=5, device="cuda"):
+        self.device = torch.device(device)
+        L, H, P = (int(v) for v in weights["meta"])
+        self.W = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in weights.items() if k != "meta"}
+        self.layers, self.heads, self.patch, self.n_surgery = L, H, P, n_surgery
+        self.width = self.W["conv1.weight"].shape[0]
+        self.embed = self.W["proj"].shape[1]
+        self.grid0 = int(round((self.W["positional_embedding"].shape[0] - 1) ** 0.5))
+        self._blocks = (_lib.VitLayer * L)()
+        for i in range(L):
+            for f, name in _BLOCK_FIELDS:
+                setattr(self._blocks[i], f, self.W["blocks.%d.%s" % (i, name)].data_ptr())
+        w = _lib.VitWeights()
+        w.layers, w.width, w.heads, w.patch, w.embed, w.grid0, w.n_surgery = L, self.width, H, P, self.embed, self.grid0, n_surgery
+        for f, name in (("conv1", "conv1.weight"), ("cls", "class_embedding"), ("pos", "positional_embedding"),
+                        ("ln_pre_w", "ln_pre.weight"), ("ln_pre_b", "ln_pre.bias"), ("ln_post_w", "ln_post.weight"),
+                        ("ln_post_b", "ln_post.bias"), ("proj", "proj")):
+            setattr(w, f, self.W[name].data_ptr())
+        w.blocks = ctypes.cast(self._blocks, ctypes.POINTER(_lib.VitLayer))
+        self._w = w
+        self._ws = None
+
+    @classmethod
+    def from_visual(cls, visual, n_surgery=5, device="cuda"):
+        return cls(pack_from_visual(visual), n_surgery, device)
+
+    @torch.no_grad()
+    def forward(self, img):
+        """img [B,3,S,S] -> (tokens [B,N,E] un-normalised, attn [L,B,N,N], feats [L,B,N,D])."""
+        img = img.to(self.device, torch.float32)
+        if img.stride(-1) != 1:
+            img = img.contiguous()
+        B, C, S, S2 = img.shape
+        if C != 3 or S != S2:
+            raise RuntimeError(f"SurgeryViT: expected [B,3,S,S] square images, got {tuple(img.shape)}")
+        if S % self.patch:
+            raise RuntimeError(f"SurgeryViT: image size {S} is not a multiple of the patch size {self.patch}")
+        N = (S // self.patch) ** 2 + 1
+        nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
+        if self._ws is None or self._ws.numel() * 4 < nbytes:
+            self._ws = None
+            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+        tokens = torch.empty((B, N, self.embed), dtype=torch.float32, device=self.device)
+        attn = torch.empty((self.layers, B, N, N), dtype=torch.float32, device=self.device)
+        feats = torch.empty((self.layers, B, N, self.width), dtype=torch.float32, device=self.device)
+        _lib.call("excel_vit_forward", ctypes.byref(self._w), _lib.ptr(img), img.stride(0), img.stride(1), img.stride(2), B, S,
+                  _lib.ptr(self._ws), self._ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.stream())
+        return tokens, attn, feats
+
+    __call__ = forward
+
+
+_ENGINES = {}
+
+
+def engine_for(model, n_surgery=5):
+    """SurgeryViT for a reference ``ExCEL_CLIP`` (or its ``.visual``); cached per module and weight version."""
+    if isinstance(model, SurgeryViT):
+        return model
+    visual = getattr(model, "visual", model)
+    key = id(visual)
+    ver = tuple((p.data_ptr(), p._version) for p in visual.parameters())
+    hit = _ENGINES.get(key)
+    if hit is None or hit[0] != ver:
+        _ENGINES[key] = (ver, SurgeryViT.from_visual(visual, n_surgery))
+    return _ENGINES[key][1]
+
+
+def generate_clip_fts(inputs, model, return_weights=True, ex_feats=None):
+    """clip/clip.py:348-358: (image_features [B,N,E] normalised over the TOKEN axis, attn_weights [L,B,N,N],
+    all_feats [L,B,N,D]).  ``model``: a SurgeryViT, or the reference's ExCEL_CLIP module."""
+    if ex_feats is not None:
+        raise NotImplementedError("excel_b200: generate_clip_fts(ex_feats=...) (LVC branch) is SURVEY §8(f1), not built yet")
+    tokens, attn, feats = engine_for(model)(inputs)
+    return token_normalize(tokens), attn, feats

@@ -101,6 +101,34 @@ int excel_token_normalize(const float* tok, int B, int N, int E, float* norm_ws,
 int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, float* S_ws, float* out,
                       void* stream);
 
+/* ---------------------------------------------------------------- ViT (clip/clip_surgery_model.py) */
+
+/* Weights of one ResidualAttentionBlock (clip/clip_surgery_model.py:285-337); all device pointers, fp32,
+ * nn.Linear layout [out,in].  in_w/in_b = attn.in_proj (or the surgery Attention's qkv, a clone of it,
+ * :396-405); out_w/out_b = attn.out_proj (or Attention.proj). */
+typedef struct {
+    const float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+} ExcelVitLayer;
+
+/* VisionTransformer (clip/clip_surgery_model.py:374-448).  conv1 [width, 3*patch*patch]; cls [width];
+ * pos [1+grid0^2, width]; proj [width, embed]; blocks: HOST array of `layers` entries.  The last
+ * n_surgery blocks run the dual-path surgery attention (reload_self_attn(layers=6) -> 5, :399). */
+typedef struct {
+    int layers, width, heads, patch, embed, grid0, n_surgery;
+    const float *conv1, *cls, *pos, *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b, *proj;
+    const ExcelVitLayer* blocks;
+} ExcelVitWeights;
+
+int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int heads);
+
+/* VisionTransformer.forward + Transformer.forward (clip/clip_surgery_model.py:418-448, 346-371) as called by
+ * clip.generate_clip_fts (clip/clip.py:348-358), for img [B,3,S,S] (element strides b, c, y; x contiguous).
+ * Outputs: tokens [B,N,embed] (BEFORE the token-axis normalisation of clip.py:353 -> excel_token_normalize),
+ * attn [layers,B,N,N], feats [layers,B,N,width] with the reference's view aliasing. */
+int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_stride_b, int64_t img_stride_c,
+                      int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes, float* tokens,
+                      float* attn, float* feats, void* stream);
+
 /* ---------------------------------------------------------------- dense fp32 GEMM ------------- */
 
 /* C[b] = act(alpha * A[b] * op(B[b]) + bias) + residual[b]; exact fp32 (SIMT).  A [M,K] (lda); B [N,K] (ldb)
