@@ -19,6 +19,8 @@ SIGNATURES = {
     "excel_last_error": ([], _c.c_char_p),
     "excel_version": ([], _i),
     "excel_device_arch": ([_i], _i),
+    "excel_launch_count": ([], _i64),
+    "excel_confusion_hist": ([_p, _p, _i64, _i, _p, _p], _i),
     "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
     "excel_svc_mean_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),

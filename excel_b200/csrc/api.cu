@@ -15,7 +15,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;  // kernels enqueued by this library (single host thread per process)
+
 int check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) return 0;
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -25,6 +28,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* excel_last_error(void) { return xl::g_err; }
 extern "C" int excel_version(void) { return 1; }
+extern "C" int64_t excel_launch_count(void) { return (int64_t)xl::g_launches; }
 extern "C" int excel_device_arch(int device) {
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) {

@@ -25,6 +25,7 @@ extern "C" {
 const char* excel_last_error(void);
 int excel_version(void);              /* 100*major + minor */
 int excel_device_arch(int device);    /* 10*major + minor of `device` (100 on B200), <0 on error */
+int64_t excel_launch_count(void);     /* kernels this library has enqueued so far in this process */
 
 /* ---------------------------------------------------------------- PAR (utils/PAR.py) ---------- */
 
@@ -128,6 +129,13 @@ int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int heads);
 int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_stride_b, int64_t img_stride_c,
                       int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes, float* tokens,
                       float* attn, float* feats, void* stream);
+
+/* ---------------------------------------------------------------- metric (utils/evaluate.py) --- */
+
+/* utils/evaluate.py:9-15 (_fast_hist), accumulated on the device: hist[nc*t + p] += 1 over n pixels with
+ * 0 <= t < nc (other labels, e.g. 255 = ignore, are skipped).  hist: int64 [nc*nc], NOT cleared here. */
+int excel_confusion_hist(const int64_t* label_true, const int64_t* label_pred, int64_t n, int num_classes,
+                         int64_t* hist, void* stream);
 
 /* ---------------------------------------------------------------- dense fp32 GEMM ------------- */
 

@@ -64,30 +64,7 @@ def export_visual_weights(visual):
     return W
 
 
-def random_visual_weights(layers=12, width=768, patch=16, grid0=14, embed=512, seed=0, sharpen=1.0):
-    """Seeded random weight pack with CLIP-like initial scales (no checkpoint is available);
-    used where the reference is not importable (GPU box) so bench/tests need no fixture file."""
-    g = torch.Generator().manual_seed(seed)
-    rn = lambda *s, std=1.0: (torch.randn(*s, generator=g) * std)
-    W = {"conv1.weight": rn(width, 3, patch, patch, std=(3 * patch * patch) ** -0.5),
-         "class_embedding": rn(width, std=width ** -0.5),
-         "positional_embedding": rn(grid0 * grid0 + 1, width, std=width ** -0.5),
-         "proj": rn(width, embed, std=width ** -0.5)}
-    for n in ("ln_pre", "ln_post"):
-        W[n + ".weight"], W[n + ".bias"] = 1 + rn(width, std=0.05), rn(width, std=0.02)
-    for i in range(layers):
-        o = "blocks.%d." % i
-        W[o + "in_proj_weight"] = rn(3 * width, width, std=width ** -0.5) * sharpen
-        W[o + "in_proj_bias"] = rn(3 * width, std=0.02)
-        W[o + "out_proj.weight"] = rn(width, width, std=width ** -0.5 * (2 * layers) ** -0.5)
-        W[o + "out_proj.bias"] = rn(width, std=0.02)
-        for n in ("ln_1", "ln_2"):
-            W[o + n + ".weight"], W[o + n + ".bias"] = 1 + rn(width, std=0.05), rn(width, std=0.02)
-        W[o + "c_fc.weight"], W[o + "c_fc.bias"] = rn(4 * width, width, std=(2 * width) ** -0.5), rn(4 * width, std=0.02)
-        W[o + "c_proj.weight"] = rn(width, 4 * width, std=width ** -0.5 * (2 * layers) ** -0.5)
-        W[o + "c_proj.bias"] = rn(width, std=0.02)
-    W["meta"] = torch.tensor([layers, width // 64, patch], dtype=torch.int64)
-    return W
+from excel_b200.synth import random_visual_weights  # noqa: E402,F401  (one seeded definition for oracle and CUDA path)
 
 
 # --------------------------------------------------------------------------- ViT (a3-a7)
