@@ -32,7 +32,9 @@ SIGNATURES = {
     "excel_token_normalize": ([_p, _i, _i, _i, _p, _p, _p], _i),
     "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _p, _p], _i),
     "excel_vit_workspace_bytes": ([_i, _i, _i, _i, _i], _i64),
+    "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
     "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p], _i),
+    "excel_gemm_tc": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _p], _i),
     "excel_sgemm": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _i64, _i64, _i64, _f, _i, _i, _p], _i),
 }
 
@@ -40,12 +42,13 @@ SIGNATURES = {
 
 class VitLayer(ctypes.Structure):
     _fields_ = [(n, _p) for n in ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b",
-                                  "proj_w", "proj_b")]
+                                  "proj_w", "proj_b", "in_ws", "out_ws", "fc_ws", "proj_ws")]
 
 
 class VitWeights(ctypes.Structure):
     _fields_ = [(n, _i) for n in ("layers", "width", "heads", "patch", "embed", "grid0", "n_surgery")] + \
-               [(n, _p) for n in ("conv1", "cls", "pos", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj")] + \
+               [(n, _p) for n in ("conv1", "cls", "pos", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj", "conv1_s",
+                                  "proj_t_s")] + \
                [("blocks", ctypes.POINTER(VitLayer))]
 
 

@@ -1,0 +1,302 @@
+// tcgen05 GEMM engine for the encoder's dense contractions (linear layers, q k^T, P V) on sm_100a.
+//
+// Precision: the reference is fp32 end to end (clip/build_model.py:72) and the parity bar is 1e-3 on
+// min-max-normalised CAMs through 12 layers, which single-pass TF32/BF16 misses (measured on the oracle:
+// 4e-3 / 2e-2).  Operands are therefore SPLIT fp16 pairs x = hi + lo (hi = fp16(x), lo = fp16(x - hi),
+// 22 significant bits) and every tile computes  A_hi B_hi + A_hi B_lo + A_lo B_hi  with fp32
+// accumulation in TMEM: fp32-quality products (rel. error ~7e-7) at three tensor-core passes, and only
+// four tile loads per k-block (each operand half is reused by two of the three MMAs).
+//
+// Split matrices are row-major fp16 [rows, 2*Kp]: columns [0,K) hold hi, [Kp, Kp+K) hold lo, Kp a multiple
+// of 64, padding zero.  Both operands are K-major ("TN": C[m,n] = sum_k A[m,k] B[n,k]), i.e. activations
+// [tokens, features] against nn.Linear weights [out, in], q against k, P against V^T.
+//
+// Kernel anatomy (one 128x128 output tile per CTA, 192 threads):
+//   warp 0   : TMA producer -- 4 boxes (A_hi, A_lo, B_hi, B_lo; 64 k x 128 rows, 128B swizzle) per stage,
+//              3-stage mbarrier ring (64 KB / stage);
+//   warp 1   : allocates 128 TMEM columns, one lane issues 12 tcgen05.mma (M128 N128 K16, kind::f16) per
+//              stage and tcgen05.commit's the stage back to the producer / the accumulator to the epilogue;
+//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns per instruction, alpha / bias / QuickGELU /
+//              residual in registers, fp32 and/or split-fp16 stores.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "excel_b200.h"
+#include "gemm_tc.cuh"
+#include "ptx.cuh"
+
+namespace xl {
+
+constexpr int kBM = 128, kBK = 64, kTcStages = 3;
+constexpr uint32_t kTileBytes = kBM * kBK * 2;        // one 128-row x 64-k fp16 tile: 16 KB
+constexpr uint32_t kStageBytes = 4 * kTileBytes;      // A_hi, A_lo, B_hi, B_lo (B tiles use BN*128 B of their slot)
+constexpr int kTcThreads = 192;
+constexpr size_t kTcSmem = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---- tcgen05 / TMEM PTX -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA shared-memory descriptor.
+// start address >> 4 | LBO (unused for swizzled K-major: 1) << 16 | SBO = 1024 B >> 4 << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = BN
+__host__ __device__ constexpr uint32_t make_idesc(int bn) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+template <int kBN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024 B alignment
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kTcStages * kStageBytes);
+    uint64_t* empty_bar = full_bar + kTcStages;
+    uint64_t* accum_bar = empty_bar + kTcStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
+    const int z1 = blockIdx.z / p.nb2, z2 = blockIdx.z % p.nb2;
+    constexpr uint32_t kIdesc = make_idesc(kBN);
+    constexpr uint32_t kTxBytes = 2 * kTileBytes + 2 * kBN * kBK * 2;
+    const int a_row = p.a_row0 + z1 * p.a_row1 + z2 * p.a_row2 + m0, a_col = p.a_col0 + z1 * p.a_col1 + z2 * p.a_col2;
+    const int b_row = p.b_row0 + z1 * p.b_row1 + z2 * p.b_row2 + n0, b_col = p.b_col0 + z1 * p.b_col1 + z2 * p.b_col2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kBN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int s = kb % kTcStages;
+                mbar_wait(&empty_bar[s], ((kb / kTcStages) & 1) ^ 1);
+                uint8_t* st = tiles + s * kStageBytes;
+                mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
+                tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
+                tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
+                tma_load_2d(st + 2 * kTileBytes, &tmB, &full_bar[s], b_col + kb * kBK, b_row);
+                tma_load_2d(st + 3 * kTileBytes, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+                const int s = kb % kTcStages;
+                mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
+                tc_fence_after();
+                const uint32_t st = smem_u32(tiles + s * kStageBytes);
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
+                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 fp16 = 32 B further along K inside the swizzle atom
+                    umma_f16(tmem_base, a_hi + adv, b_lo + adv, kIdesc, (kb | k) != 0);
+                    umma_f16(tmem_base, a_lo + adv, b_hi + adv, kIdesc, 1);
+                    umma_f16(tmem_base, a_hi + adv, b_hi + adv, kIdesc, 1);
+                }
+                umma_commit(&empty_bar[s]);  // stage s may be refilled once these MMAs have read it
+            }
+            umma_commit(accum_bar);          // accumulator complete
+        }
+    } else {
+        // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 == output rows m0 + 32*(w%4) + lane
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int lg = warp & 3;
+        const int m = m0 + lg * 32 + lane;
+        const bool row_ok = m < p.M;
+        const int64_t coff = (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2 + (int64_t)m * p.ldc;
+        const int64_t soff = (int64_t)z1 * p.cs1 + (int64_t)z2 * p.cs2 + (int64_t)m * p.lds;
+#pragma unroll 1
+        for (int c = 0; c < kBN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
+            const int nb = n0 + c * 32;
+            if (!row_ok || nb >= p.N) continue;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float t = p.alpha * __uint_as_float(r[j]);
+                if (p.bias && nb + j < p.N) t += __ldg(p.bias + nb + j);
+                if (p.act == 1) t = t * (1.f / (1.f + expf(-1.702f * t)));  // QuickGELU
+                v[j] = t;
+            }
+            if (p.C) {
+                float* dst = p.C + coff + nb;
+                const float* res = p.residual ? p.residual + coff + nb : nullptr;
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                    (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (res) {
+                            const float4 q = *reinterpret_cast<const float4*>(res + j);
+                            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+                        }
+                        *reinterpret_cast<float4*>(dst + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < p.N) dst[j] = v[j] + (res ? res[j] : 0.f);
+                }
+            }
+            if (p.Cs) {  // split-fp16 copy of the result (operand of the next GEMM); no residual on this path
+                __half* hi = p.Cs + soff + nb;
+                __half* lo = hi + p.cs_lo_off;
+                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(hi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __align__(16) __half h[8], l[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            h[e] = __float2half_rn(v[j + e]);
+                            l[e] = __float2half_rn(v[j + e] - __half2float(h[e]));
+                        }
+                        *reinterpret_cast<uint4*>(hi + j) = *reinterpret_cast<const uint4*>(h);
+                        *reinterpret_cast<uint4*>(lo + j) = *reinterpret_cast<const uint4*>(l);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < p.N) {
+                            const __half h = __float2half_rn(v[j]);
+                            hi[j] = h;
+                            lo[j] = __float2half_rn(v[j] - __half2float(h));
+                        }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kBN);
+    }
+}
+
+// ---- fp32 -> split fp16 ---------------------------------------------------------------------------------
+// out [rows, 2*Kp] : hi | lo, zero padded to Kp columns each
+__global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, int Kp, __half* __restrict__ out,
+                                 float scale) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= Kp) return;
+    float v = c < cols ? x[(int64_t)r * ldx + c] * scale : 0.f;
+    const __half h = __float2half_rn(v);
+    out[(int64_t)r * 2 * Kp + c] = h;
+    out[(int64_t)r * 2 * Kp + Kp + c] = __float2half_rn(v - __half2float(h));
+}
+
+int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols_total, int64_t ld_elems, int box_rows) {
+    const uint64_t dims[2] = {(uint64_t)cols_total, (uint64_t)rows};
+    const uint64_t strides[1] = {(uint64_t)ld_elems * 2};
+    const uint32_t box[2] = {kBK, (uint32_t)box_rows};
+    return encode_tensor_map(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        attr_set = true;
+    }
+    XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1, "tc_gemm: bad shape M=%d N=%d kblocks=%d", p.M, p.N, p.kblocks);
+    XL_REQUIRE(bn == 64 || bn == 128, "tc_gemm: tile N must be 64 or 128 (the B tensor map's box must match)");
+    XL_REQUIRE(batch <= 65535 && ceil_div(p.M, kBM) <= 65535, "tc_gemm: grid too large");
+    dim3 grid(ceil_div(p.N, bn), ceil_div(p.M, kBM), batch);
+    if (bn == 128) gemm_tc_kernel<128><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, p);
+    else gemm_tc_kernel<64><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, p);
+    return check_launch("gemm_tc_kernel");
+}
+
+int split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, __half* out, cudaStream_t st, float scale) {
+    XL_REQUIRE(rows >= 0 && cols >= 0 && Kp >= cols && Kp % 64 == 0, "split_f16: bad shape");
+    if (rows == 0) return 0;
+    // rows ride on grid.y (<= 65535): fold larger row counts into several launches
+    for (int r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        dim3 grid(ceil_div(Kp, 256), nr);
+        split_f16_kernel<<<grid, 256, 0, st>>>(x + (int64_t)r0 * ldx, ldx, nr, cols, Kp, out + (int64_t)r0 * 2 * Kp, scale);
+        if (int e = check_launch("split_f16_kernel")) return e;
+    }
+    return 0;
+}
+
+}  // namespace xl
+
+using namespace xl;
+
+// Stand-alone entry point (tests, small callers): C = alpha * A B^T (+bias, act, +residual) for fp32 row-major
+// A [M,K], B [N,K]; operands are split to fp16 pairs into ws (>= 2*(M+N)*Kp halves, Kp = round_up(K,64)).
+extern "C" int excel_gemm_tc(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N,
+                             int K, int64_t lda, int64_t ldb, int64_t ldc, float alpha, int act, void* ws, int64_t ws_bytes,
+                             void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    XL_REQUIRE(M >= 1 && N >= 1 && K >= 1, "gemm_tc: bad shape");
+    const int Kp = (K + 63) & ~63;
+    XL_REQUIRE(ws_bytes >= (int64_t)2 * (M + N) * Kp * 2, "gemm_tc: workspace too small");
+    __half* As = reinterpret_cast<__half*>(ws);
+    __half* Bs = As + (int64_t)M * 2 * Kp;
+    if (int e = split_f16(A, lda, M, K, Kp, As, st)) return e;
+    if (int e = split_f16(B, ldb, N, K, Kp, Bs, st)) return e;
+    CUtensorMap tmA, tmB;
+    const int bn = N <= 64 ? 64 : 128;
+    if (int e = make_operand_map(&tmA, As, M, 2 * Kp, 2 * Kp, 128)) return e;
+    if (int e = make_operand_map(&tmB, Bs, N, 2 * Kp, 2 * Kp, bn)) return e;
+    TcParams p = {};
+    p.M = M; p.N = N; p.kblocks = Kp / 64; p.a_lo_off = Kp; p.b_lo_off = Kp; p.nb2 = 1;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.alpha = alpha; p.act = act;
+    return tc_gemm(tmA, tmB, p, 1, bn, st);
+}

@@ -9,22 +9,40 @@
 // The aliasing falls out of the buffer plan: every block writes its state straight into feats[l], and the
 // surgery blocks update feats[l-1] / feats[first-1] in place exactly where the reference's in-place `+=`
 // mutates the views it had already appended.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "excel_b200.h"
+#include "gemm_tc.cuh"
 
 namespace xl {
 
-// ---- patch embedding: im2col (conv1 16x16/16, no bias == GEMM; clip_surgery_model.py:421) ------------
+// Probabilities (<= 1, mostly ~1/N) are scaled by 2^10 before the fp16 split so that hi/lo stay clear of fp16's
+// subnormal range (absolute resolution 6e-8); the exact factor 2^-10 is folded into the GEMM's alpha.
+constexpr float kProbScale = 1024.f;
+
+__device__ __forceinline__ void split_store(__half* hi, __half* lo, float v) {
+    const __half h = __float2half_rn(v);
+    *hi = h;
+    *lo = __float2half_rn(v - __half2float(h));
+}
+
+// ---- patch embedding: im2col (conv1 16x16/16, no bias == GEMM; clip_surgery_model.py:421), split-fp16 ----
 __global__ void im2col_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, int S, int P, int g,
-                              float* __restrict__ col) {
-    // col[(b*g*g + py*g + px), c*P*P + iy*P + ix] = img[b, c, py*P+iy, px*P+ix]
-    const int kk = blockIdx.x * blockDim.x + threadIdx.x;  // column in [0, 3*P*P)
+                              __half* __restrict__ col, int KKp) {
+    // col[(b*g*g + py*g + px), c*P*P + iy*P + ix] = img[b, c, py*P+iy, px*P+ix]   (hi | lo halves, KKp apart)
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;  // column in [0, KKp)
     const int p = blockIdx.y, b = blockIdx.z;
     const int KK = 3 * P * P;
-    if (kk >= KK) return;
-    const int c = kk / (P * P), r = kk - c * P * P, iy = r / P, ix = r - iy * P;
-    const int py = p / g, px = p - py * g;
-    col[((int64_t)b * g * g + p) * KK + kk] = img[(int64_t)b * sb + (int64_t)c * sc + (int64_t)(py * P + iy) * sy + px * P + ix];
+    if (kk >= KKp) return;
+    float v = 0.f;
+    if (kk < KK) {
+        const int c = kk / (P * P), r = kk - c * P * P, iy = r / P, ix = r - iy * P;
+        const int py = p / g, px = p - py * g;
+        v = img[(int64_t)b * sb + (int64_t)c * sc + (int64_t)(py * P + iy) * sy + px * P + ix];
+    }
+    __half* row = col + ((int64_t)b * g * g + p) * 2 * KKp;
+    split_store(row + kk, row + KKp + kk, v);
 }
 
 // ---- positional embedding, bilinear align_corners=False from g0 x g0 to g x g (:426-435) -------------
@@ -52,13 +70,14 @@ __global__ void pos_resize_kernel(const float* __restrict__ pos, int g0, int g, 
 template <bool EMBED>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bvec,
-                 float* __restrict__ y, int64_t rows, int D, int N, const float* __restrict__ cls,
-                 const float* __restrict__ pos) {
+                 float* __restrict__ y, __half* __restrict__ ys, int64_t rows, int D, int N,
+                 const float* __restrict__ cls, const float* __restrict__ pos) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const float* xr = x + row * D;
-    float* yr = y + row * D;
+    float* yr = y ? y + row * D : nullptr;
+    __half* sr = ys ? ys + row * 2 * D : nullptr;  // split-fp16 copy (operand of the next GEMM): hi | lo, D apart
     const int n = EMBED ? (int)(row % N) : 0;
     constexpr int MAXV = 32;  // D <= 1024
     float v[MAXV];
@@ -86,13 +105,17 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int d = lane + 32 * i;
-        if (d < D) yr[d] = (v[i] - mean) * rstd * w[d] + bvec[d];
+        if (d < D) {
+            const float o = (v[i] - mean) * rstd * w[d] + bvec[d];
+            if (yr) yr[d] = o;
+            if (sr) split_store(sr + d, sr + D + d, o);
+        }
     }
 }
 
-// ---- row softmax in place (rows of length n); one 128-thread block per row ----------------------------
+// ---- row softmax in place (rows of length n) + split-fp16 copy P_s [rows, 2*np] (zero padded) -----------
 __global__ void __launch_bounds__(128)
-softmax_rows_kernel(float* __restrict__ S, int n) {
+softmax_rows_kernel(float* __restrict__ S, int n, __half* __restrict__ Ps, int np) {
     __shared__ float red[32];
     float* row = S + (int64_t)blockIdx.x * n;
     float mx = -INFINITY;
@@ -105,7 +128,41 @@ softmax_rows_kernel(float* __restrict__ S, int n) {
         sum += e;
     }
     sum = block_reduce(sum, red, OpSum(), 0.f);
-    for (int j = threadIdx.x; j < n; j += 128) row[j] = row[j] / sum;
+    __half* ph = Ps + (int64_t)blockIdx.x * 2 * np;
+    for (int j = threadIdx.x; j < np; j += 128) {
+        float v = 0.f;
+        if (j < n) {
+            v = row[j] / sum;
+            row[j] = v;
+        }
+        split_store(ph + j, ph + np + j, v * kProbScale);
+    }
+}
+
+// ---- V^T: vt[(b*D + c), token] from the V block of qkv_s, split halves, zero padded to np tokens -------------
+__global__ void __launch_bounds__(1024)
+vt_kernel(const __half* __restrict__ qkv, int N, int D, int np, __half* __restrict__ vt) {
+    __shared__ __half th[32][33], tl[32][33];
+    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    {
+        const int n = n0 + ty, c = c0 + tx;
+        __half h = __float2half_rn(0.f), l = h;
+        if (n < N) {
+            const __half* r = qkv + ((int64_t)b * N + n) * 6 * D;
+            h = r[2 * D + c];
+            l = r[3 * D + 2 * D + c];
+        }
+        th[ty][tx] = h;
+        tl[ty][tx] = l;
+    }
+    __syncthreads();
+    const int c = c0 + ty, n = n0 + tx;
+    if (n < np) {
+        __half* o = vt + ((int64_t)b * D + c) * 2 * np;
+        o[n] = th[tx][ty];
+        o[np + n] = tl[tx][ty];
+    }
 }
 
 // ---- out[b,i,j] (+)= coef * sum_h P[b,h,i,j] ------------------------------------------------------------
@@ -127,41 +184,102 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
     if (d < D) dst[(int64_t)b * stride_b + d] = src[(int64_t)b * stride_b + d];
 }
 
-struct Ws {  // workspace carve-up (floats)
-    float *col, *pos, *h, *qkv, *S, *pnew, *o, *o2, *mid, *u, *x0;
+struct Ws {  // workspace carve-up
+    float *pos, *S, *pnew, *mid, *x0;
+    __half *col, *h, *qkv, *vt, *P, *pn, *o, *o2, *u;
 };
 
-static size_t ws_floats(int B, int N, int D, int H, int KK) {
-    const size_t BN = (size_t)B * N;
-    return (size_t)B * (N - 1) * KK + (size_t)N * D + BN * D + BN * 3 * D + (size_t)B * H * N * N + (size_t)B * N * N +
-           BN * D * 4 + BN * 4 * D + 64;
+static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
+    const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
+    size_t t = 0;
+    t += align256((size_t)N * D * 4);                 // pos
+    t += align256((size_t)B * H * N * N * 4);         // S
+    t += align256((size_t)B * N * N * 4);             // pnew
+    t += 2 * align256(BN * D * 4);                    // mid, x0
+    t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
+    t += 3 * align256(BN * 2 * D * 2);                // h, o, o2
+    t += align256(BN * 6 * D * 2);                    // qkv
+    t += align256((size_t)B * D * 2 * np * 2);        // vt
+    t += align256((size_t)B * H * N * 2 * np * 2);    // P
+    t += align256(BN * 2 * np * 2);                   // pn
+    t += align256(BN * 8 * D * 2);                    // u
+    return t + 256;
 }
 
-static int layernorm(const float* x, const float* w, const float* b, float* y, int64_t rows, int D, cudaStream_t st) {
-    layernorm_kernel<false><<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(x, w, b, y, rows, D, 1, nullptr, nullptr);
+struct Maps {  // tensor maps of the activation operands (built once per forward)
+    CUtensorMap col, h, qkv_a, qkv_b, vt64, vt128, P, pn, o, o2, u;
+};
+
+struct Ctx {
+    int B, N, D, H, dh, np, L;
+    int64_t BN;
+    Ws w;
+    Maps m;
+    cudaStream_t st;
+};
+
+static int layernorm(const Ctx& c, const float* x, const float* w, const float* b, __half* ys) {
+    layernorm_kernel<false><<<(unsigned)ceil_div64(c.BN, 8), 256, 0, c.st>>>(x, w, b, nullptr, ys, c.BN, c.D, 1, nullptr, nullptr);
     return check_launch("layernorm_kernel");
 }
 
-// y = act(x W^T + bias) + residual   (x [M,K], W [Nout,K])
-static int linear(const float* x, const float* W, const float* bias, const float* residual, float* y, int M, int Nout,
-                  int K, int act, cudaStream_t st) {
-    return sgemm2(x, W, y, bias, residual, M, Nout, K, K, K, Nout, 1, 0, 0, 0, 1, 0, 0, 0, 1.f, 1, act, st);
+// y = act(x W^T + bias) (+ residual): x split [M, 2K] (map ma), W split [Nout, 2K] (map mw)
+static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, int K, int Nout, const float* bias, int act,
+                  const float* residual, float* y, __half* ys) {
+    TcParams p = {};
+    p.M = (int)c.BN; p.N = Nout; p.kblocks = K / 64; p.a_lo_off = K; p.b_lo_off = K; p.nb2 = 1;
+    p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f; p.act = act;
+    p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
+    return tc_gemm(ma, mw, p, 1, 128, c.st);
 }
 
-// S[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks of qkv (offsets xo, yo into the 3D row)
-static int scores(const float* qkv, int xo, int yo, float* S, int B, int N, int D, int H, float scale, cudaStream_t st) {
-    const int dh = D / H;
-    if (int e = sgemm2(qkv + xo, qkv + yo, S, nullptr, nullptr, N, N, dh, 3 * D, 3 * D, N, B, (int64_t)N * 3 * D,
-                       (int64_t)N * 3 * D, (int64_t)H * N * N, H, dh, dh, (int64_t)N * N, scale, 1, 0, st)) return e;
-    softmax_rows_kernel<<<(unsigned)((int64_t)B * H * N), 128, 0, st>>>(S, N);
+// S[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s; also P_s
+static int scores(const Ctx& c, int xo, int yo, float scale) {
+    TcParams p = {};
+    p.M = c.N; p.N = c.N; p.kblocks = c.dh / 64; p.a_lo_off = 3 * c.D; p.b_lo_off = 3 * c.D; p.nb2 = c.H;
+    p.a_row1 = c.N; p.a_col0 = xo; p.a_col2 = c.dh;
+    p.b_row1 = c.N; p.b_col0 = yo; p.b_col2 = c.dh;
+    p.C = c.w.S; p.ldc = c.N; p.c1 = (int64_t)c.H * c.N * c.N; p.c2 = (int64_t)c.N * c.N; p.alpha = scale;
+    if (int e = tc_gemm(c.m.qkv_a, c.m.qkv_b, p, c.B * c.H, 128, c.st)) return e;
+    softmax_rows_kernel<<<(unsigned)((int64_t)c.B * c.H * c.N), 128, 0, c.st>>>(c.w.S, c.N, c.w.P, c.np);
     return check_launch("softmax_rows_kernel");
 }
 
-static int head_reduce(const float* P, float* out, int B, int H, int N, float coef, int accumulate, cudaStream_t st) {
-    const int64_t nn = (int64_t)N * N;
-    dim3 grid((unsigned)ceil_div64(nn, 256), B);
-    head_reduce_kernel<<<grid, 256, 0, st>>>(P, out, H, nn, coef, accumulate);
+// o_s[b, :, h*dh..] = P[b,h] V[b,h]   (split output feeding the out projection)
+static int attn_v(const Ctx& c) {
+    TcParams p = {};
+    p.M = c.N; p.N = c.dh; p.kblocks = c.np / 64; p.a_lo_off = c.np; p.b_lo_off = c.np; p.nb2 = c.H;
+    p.a_row1 = c.H * c.N; p.a_row2 = c.N;
+    p.b_row1 = c.D; p.b_row2 = c.dh;
+    p.alpha = 1.f / kProbScale;
+    p.Cs = c.w.o; p.lds = 2 * c.D; p.cs1 = (int64_t)c.N * 2 * c.D; p.cs2 = c.dh; p.cs_lo_off = c.D;
+    return tc_gemm(c.m.P, c.m.vt64, p, c.B * c.H, 64, c.st);
+}
+
+static int head_reduce(const Ctx& c, float* out, float coef, int accumulate) {
+    const int64_t nn = (int64_t)c.N * c.N;
+    dim3 grid((unsigned)ceil_div64(nn, 256), c.B);
+    head_reduce_kernel<<<grid, 256, 0, c.st>>>(c.w.S, out, c.H, nn, coef, accumulate);
     return check_launch("head_reduce_kernel");
+}
+
+// ln_1 -> in_proj -> split qkv, V^T
+static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in) {
+    if (int e = layernorm(c, src, Lw.ln1_w, Lw.ln1_b, c.w.h)) return e;
+    if (int e = linear(c, c.m.h, m_in, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv)) return e;
+    dim3 grid(ceil_div(c.np, 32), c.D / 32, c.B), block(32, 32);
+    vt_kernel<<<grid, block, 0, c.st>>>(c.w.qkv, c.N, c.D, c.np, c.w.vt);
+    return check_launch("vt_kernel");
+}
+
+// feat = mid + c_proj(QuickGELU(c_fc(ln_2(mid))))
+static int mlp_stage(const Ctx& c, const float* mid, const ExcelVitLayer& Lw, const CUtensorMap& m_fc, const CUtensorMap& m_proj,
+                     float* feat) {
+    if (int e = layernorm(c, mid, Lw.ln2_w, Lw.ln2_b, c.w.h)) return e;
+    if (int e = linear(c, c.m.h, m_fc, c.D, 4 * c.D, Lw.fc_b, 1, nullptr, nullptr, c.w.u)) return e;
+    return linear(c, c.m.u, m_proj, 4 * c.D, c.D, Lw.proj_b, 0, mid, feat, nullptr);
 }
 
 }  // namespace xl
@@ -170,7 +288,11 @@ using namespace xl;
 
 extern "C" int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int heads) {
     const int g = S / patch, N = g * g + 1;
-    return (int64_t)(ws_floats(B, N, D, heads, 3 * patch * patch) * sizeof(float));
+    return (int64_t)ws_bytes(B, N, D, heads, (3 * patch * patch + 63) & ~63);
+}
+
+extern "C" int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, void* out, void* stream) {
+    return split_f16(x, ldx, rows, cols, Kp, reinterpret_cast<__half*>(out), (cudaStream_t)stream);
 }
 
 extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, int64_t img_stride_b, int64_t img_stride_c,
@@ -180,93 +302,130 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
     XL_REQUIRE(Wt != nullptr, "vit_forward: null weights");
     const int L = Wt->layers, D = Wt->width, H = Wt->heads, P = Wt->patch, E = Wt->embed, g0 = Wt->grid0,
               nsur = Wt->n_surgery;
-    XL_REQUIRE(L >= 1 && D >= 64 && D <= 1024 && H >= 1 && D % H == 0 && P >= 1 && E >= 1 && g0 >= 1,
-               "vit_forward: unsupported geometry L=%d D=%d H=%d P=%d", L, D, H, P);
+    XL_REQUIRE(L >= 1 && D >= 64 && D <= 1024 && D % 64 == 0 && H >= 1 && D / H == 64 && P >= 1 && E >= 1 && g0 >= 1,
+               "vit_forward: unsupported geometry L=%d D=%d H=%d P=%d (head dim must be 64)", L, D, H, P);
     XL_REQUIRE(nsur >= 1 && nsur < L, "vit_forward: n_surgery=%d must be in [1, L-1]", nsur);
     XL_REQUIRE(B >= 0 && S >= P && S % P == 0, "vit_forward: image size %d is not a multiple of the patch size %d", S, P);
+    XL_REQUIRE(Wt->conv1_s && Wt->proj_t_s, "vit_forward: split weights missing (excel_split_f16 at load time)");
     if (B == 0) return 0;
-    const int g = S / P, np = g * g, N = np + 1, KK = 3 * P * P, dh = D / H, first = L - nsur;
+    const int g = S / P, npatch = g * g, N = npatch + 1, KK = 3 * P * P, KKp = (KK + 63) & ~63, dh = D / H, first = L - nsur;
+    const int np = (N + 63) & ~63;
     const int64_t BN = (int64_t)B * N, ND = (int64_t)N * D;
-    XL_REQUIRE(workspace_bytes >= (int64_t)(ws_floats(B, N, D, H, KK) * sizeof(float)), "vit_forward: workspace too small");
-    XL_REQUIRE(np <= 65535 && B <= 65535 && (int64_t)B * H * N < (1ll << 31), "vit_forward: problem too large");
+    XL_REQUIRE(workspace_bytes >= (int64_t)ws_bytes(B, N, D, H, KKp), "vit_forward: workspace too small");
+    XL_REQUIRE(npatch <= 65535 && B <= 65535 && (int64_t)B * H * N < (1ll << 31) && BN * 6 * D < (1ll << 31),
+               "vit_forward: problem too large");
+    XL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vit_forward: workspace must be 256 B-aligned");
     const float scale = 1.f / sqrtf((float)dh);
 
-    Ws w;
-    float* p = workspace;
-    w.col = p;  p += (size_t)B * np * KK;
-    w.pos = p;  p += (size_t)N * D;
-    w.h = p;    p += BN * D;
-    w.qkv = p;  p += BN * 3 * D;
-    w.S = p;    p += (size_t)B * H * N * N;
-    w.pnew = p; p += (size_t)B * N * N;
-    w.o = p;    p += BN * D;
-    w.o2 = p;   p += BN * D;
-    w.mid = p;  p += BN * D;
-    w.x0 = p;   p += BN * D;
-    w.u = p;    p += BN * 4 * D;
+    Ctx c;
+    c.B = B; c.N = N; c.D = D; c.H = H; c.dh = dh; c.np = np; c.L = L; c.BN = BN; c.st = st;
+    {
+        uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
+        auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
+        c.w.pos = (float*)take((size_t)N * D * 4);
+        c.w.S = (float*)take((size_t)B * H * N * N * 4);
+        c.w.pnew = (float*)take((size_t)B * N * N * 4);
+        c.w.mid = (float*)take(BN * D * 4);
+        c.w.x0 = (float*)take(BN * D * 4);
+        c.w.col = (__half*)take((size_t)B * npatch * 2 * KKp * 2);
+        c.w.h = (__half*)take(BN * 2 * D * 2);
+        c.w.o = (__half*)take(BN * 2 * D * 2);
+        c.w.o2 = (__half*)take(BN * 2 * D * 2);
+        c.w.qkv = (__half*)take(BN * 6 * D * 2);
+        c.w.vt = (__half*)take((size_t)B * D * 2 * np * 2);
+        c.w.P = (__half*)take((size_t)B * H * N * 2 * np * 2);
+        c.w.pn = (__half*)take(BN * 2 * np * 2);
+        c.w.u = (__half*)take(BN * 8 * D * 2);
+    }
+    {
+        int e = 0;
+        e |= make_operand_map(&c.m.col, c.w.col, (int64_t)B * npatch, 2 * KKp, 2 * KKp, 128);
+        e |= make_operand_map(&c.m.h, c.w.h, BN, 2 * D, 2 * D, 128);
+        e |= make_operand_map(&c.m.qkv_a, c.w.qkv, BN, 6 * D, 6 * D, 128);
+        e |= make_operand_map(&c.m.qkv_b, c.w.qkv, BN, 6 * D, 6 * D, 128);
+        e |= make_operand_map(&c.m.vt64, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 64);
+        e |= make_operand_map(&c.m.vt128, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 128);
+        e |= make_operand_map(&c.m.P, c.w.P, (int64_t)B * H * N, 2 * np, 2 * np, 128);
+        e |= make_operand_map(&c.m.pn, c.w.pn, BN, 2 * np, 2 * np, 128);
+        e |= make_operand_map(&c.m.o, c.w.o, BN, 2 * D, 2 * D, 128);
+        e |= make_operand_map(&c.m.o2, c.w.o2, BN, 2 * D, 2 * D, 128);
+        e |= make_operand_map(&c.m.u, c.w.u, BN, 8 * D, 8 * D, 128);
+        if (e) return e;
+    }
 
     // ---- embedding: conv1 as GEMM, + cls, + pos, ln_pre (:421-438)
     {
-        dim3 grid(ceil_div(KK, 256), np, B);
-        im2col_kernel<<<grid, 256, 0, st>>>(img, img_stride_b, img_stride_c, img_stride_y, S, P, g, w.col);
+        dim3 grid(ceil_div(KKp, 256), npatch, B);
+        im2col_kernel<<<grid, 256, 0, st>>>(img, img_stride_b, img_stride_c, img_stride_y, S, P, g, c.w.col, KKp);
         if (int e = check_launch("im2col_kernel")) return e;
-        // patches of image b land in rows 1..np of x0[b]
-        if (int e = sgemm2(w.col, Wt->conv1, w.x0 + D, nullptr, nullptr, np, D, KK, KK, KK, D, B, (int64_t)np * KK, 0, ND, 1,
-                           0, 0, 0, 1.f, 1, 0, st)) return e;
+        CUtensorMap m_conv;
+        if (int e = make_operand_map(&m_conv, Wt->conv1_s, D, 2 * KKp, 2 * KKp, 128)) return e;
+        TcParams p = {};  // patches of image b land in rows 1..npatch of x0[b]
+        p.M = npatch; p.N = D; p.kblocks = KKp / 64; p.a_lo_off = KKp; p.b_lo_off = KKp; p.nb2 = 1; p.a_row1 = npatch;
+        p.C = c.w.x0 + D; p.ldc = D; p.c1 = ND; p.alpha = 1.f;
+        if (int e = tc_gemm(c.m.col, m_conv, p, B, 128, st)) return e;
         const float* pos = Wt->pos;
         if (g != g0) {
             dim3 gp(ceil_div(D, 256), N);
-            pos_resize_kernel<<<gp, 256, 0, st>>>(Wt->pos, g0, g, D, w.pos);
+            pos_resize_kernel<<<gp, 256, 0, st>>>(Wt->pos, g0, g, D, c.w.pos);
             if (int e = check_launch("pos_resize_kernel")) return e;
-            pos = w.pos;
+            pos = c.w.pos;
         }
-        layernorm_kernel<true><<<(unsigned)ceil_div64(BN, 8), 256, 0, st>>>(w.x0, Wt->ln_pre_w, Wt->ln_pre_b, w.x0, BN, D, N,
-                                                                            Wt->cls, pos);
+        layernorm_kernel<true><<<(unsigned)ceil_div64(BN, 8), 256, 0, st>>>(c.w.x0, Wt->ln_pre_w, Wt->ln_pre_b, c.w.x0, nullptr,
+                                                                            BN, D, N, Wt->cls, pos);
         if (int e = check_launch("layernorm_kernel<embed>")) return e;
     }
 
-    const float* x = w.x0;  // current single-path state (blocks before the surgery)
+    const float* x = c.w.x0;  // current single-path state (blocks before the surgery)
     for (int l = 0; l < L; ++l) {
         const ExcelVitLayer& Lw = Wt->blocks[l];
+        XL_REQUIRE(Lw.in_ws && Lw.out_ws && Lw.fc_ws && Lw.proj_ws, "vit_forward: split weights of block %d missing", l);
+        CUtensorMap m_in, m_out, m_fc, m_proj;
+        {
+            int e = 0;
+            e |= make_operand_map(&m_in, Lw.in_ws, 3 * D, 2 * D, 2 * D, 128);
+            e |= make_operand_map(&m_out, Lw.out_ws, D, 2 * D, 2 * D, 128);
+            e |= make_operand_map(&m_fc, Lw.fc_ws, 4 * D, 2 * D, 2 * D, 128);
+            e |= make_operand_map(&m_proj, Lw.proj_ws, D, 8 * D, 8 * D, 128);
+            if (e) return e;
+        }
         float* attn_l = attn + (int64_t)l * B * N * N;
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
-            if (int e = layernorm(x, Lw.ln1_w, Lw.ln1_b, w.h, BN, D, st)) return e;
-            if (int e = linear(w.h, Lw.in_w, Lw.in_b, nullptr, w.qkv, (int)BN, 3 * D, D, 0, st)) return e;
-            if (int e = scores(w.qkv, 0, D, w.S, B, N, D, H, scale, st)) return e;
-            if (int e = head_reduce(w.S, attn_l, B, H, N, 1.f / H, 0, st)) return e;  // need_weights: head mean
-            if (int e = sgemm2(w.S, w.qkv + 2 * D, w.o, nullptr, nullptr, N, dh, N, N, 3 * D, D, B, (int64_t)H * N * N,
-                               (int64_t)N * 3 * D, ND, H, (int64_t)N * N, dh, dh, 1.f, 0, 0, st)) return e;
-            if (int e = linear(w.o, Lw.out_w, Lw.out_b, x, w.mid, (int)BN, D, D, 0, st)) return e;       // x + attn
-            if (int e = layernorm(w.mid, Lw.ln2_w, Lw.ln2_b, w.h, BN, D, st)) return e;
-            if (int e = linear(w.h, Lw.fc_w, Lw.fc_b, nullptr, w.u, (int)BN, 4 * D, D, 1, st)) return e; // QuickGELU
-            if (int e = linear(w.u, Lw.proj_w, Lw.proj_b, w.mid, feat_l, (int)BN, D, 4 * D, 0, st)) return e;
+            if (int e = qkv_stage(c, x, Lw, m_in)) return e;
+            if (int e = scores(c, 0, D, scale)) return e;
+            if (int e = head_reduce(c, attn_l, 1.f / H, 0)) return e;  // need_weights: head mean
+            if (int e = attn_v(c)) return e;
+            if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
+            if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
             x = feat_l;
         } else {  // ---- surgery block (:309-330, Attention.forward :95-159)
             float* xnew = feats + (int64_t)(first - 1) * BN * D;              // new path, accumulates x_res in place
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
-            if (int e = layernorm(src, Lw.ln1_w, Lw.ln1_b, w.h, BN, D, st)) return e;
-            if (int e = linear(w.h, Lw.in_w, Lw.in_b, nullptr, w.qkv, (int)BN, 3 * D, D, 0, st)) return e;
+            if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
             for (int t = 0; t < 3; ++t) {
-                if (int e = scores(w.qkv, t * D, t * D, w.S, B, N, D, H, scale, st)) return e;
-                if (int e = head_reduce(w.S, w.pnew, B, H, N, 1.f / 3.f, t > 0, st)) return e;
+                if (int e = scores(c, t * D, t * D, scale)) return e;
+                if (int e = head_reduce(c, c.w.pnew, 1.f / 3.f, t > 0)) return e;
+            }
+            if (int e = split_f16(c.w.pnew, N, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
+            {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
+                TcParams p = {};
+                p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.b_lo_off = np; p.nb2 = 1;
+                p.a_row1 = N; p.b_row1 = D; p.alpha = 1.f / kProbScale;
+                p.Cs = c.w.o2; p.lds = 2 * D; p.cs1 = (int64_t)N * 2 * D; p.cs_lo_off = D;
+                if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
-            if (int e = scores(w.qkv, 0, D, w.S, B, N, D, H, scale, st)) return e;
-            if (int e = head_reduce(w.S, attn_l, B, H, N, 1.f, 0, st)) return e;
-            if (int e = sgemm2(w.S, w.qkv + 2 * D, w.o, nullptr, nullptr, N, dh, N, N, 3 * D, D, B, (int64_t)H * N * N,
-                               (int64_t)N * 3 * D, ND, H, (int64_t)N * N, dh, dh, 1.f, 0, 0, st)) return e;  // x_ori = attn_ori @ v
-            if (int e = sgemm2(w.pnew, w.qkv + 2 * D, w.o2, nullptr, nullptr, N, D, N, N, 3 * D, D, B, (int64_t)N * N,
-                               (int64_t)N * 3 * D, ND, 1, 0, 0, 0, 1.f, 0, 0, st)) return e;                 // x = attn @ v (all heads)
+            if (int e = scores(c, 0, D, scale)) return e;
+            if (int e = head_reduce(c, attn_l, 1.f, 0)) return e;
+            if (int e = attn_v(c)) return e;                                  // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
-            float* mid = (l == first) ? w.mid : src;
-            if (int e = linear(w.o, Lw.out_w, Lw.out_b, src, mid, (int)BN, D, D, 0, st)) return e;
-            if (int e = linear(w.o2, Lw.out_w, Lw.out_b, xnew, xnew, (int)BN, D, D, 0, st)) return e;        // x += x_res (:319,329)
-            if (int e = layernorm(mid, Lw.ln2_w, Lw.ln2_b, w.h, BN, D, st)) return e;
-            if (int e = linear(w.h, Lw.fc_w, Lw.fc_b, nullptr, w.u, (int)BN, 4 * D, D, 1, st)) return e;
-            if (int e = linear(w.u, Lw.proj_w, Lw.proj_b, mid, feat_l, (int)BN, D, 4 * D, 0, st)) return e;  // x_ori
+            float* mid = (l == first) ? c.w.mid : src;
+            if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, src, mid, nullptr)) return e;
+            if (int e = linear(c, c.m.o2, m_out, D, D, Lw.out_b, 0, xnew, xnew, nullptr)) return e;       // x += x_res (:319,329)
+            if (int e = mlp_stage(c, mid, Lw, m_fc, m_proj, feat_l)) return e;                           // x_ori
         }
     }
     // x[0] = x_ori[0] (:442), ln_post, @ proj (:445-446)
@@ -276,6 +435,11 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         copy_cls_kernel<<<grid, 256, 0, st>>>(feats + (int64_t)(L - 1) * BN * D, xnew, ND, D);
         if (int e = check_launch("copy_cls_kernel")) return e;
     }
-    if (int e = layernorm(xnew, Wt->ln_post_w, Wt->ln_post_b, w.h, BN, D, st)) return e;
-    return sgemm2(w.h, Wt->proj, tokens, nullptr, nullptr, (int)BN, E, D, D, E, E, 1, 0, 0, 0, 1, 0, 0, 0, 1.f, 0, 0, st);
+    if (int e = layernorm(c, xnew, Wt->ln_post_w, Wt->ln_post_b, c.w.h)) return e;
+    CUtensorMap m_pt;
+    if (int e = make_operand_map(&m_pt, Wt->proj_t_s, E, 2 * D, 2 * D, E <= 64 ? 64 : 128)) return e;
+    TcParams p = {};
+    p.M = (int)BN; p.N = E; p.kblocks = D / 64; p.a_lo_off = D; p.b_lo_off = D; p.nb2 = 1;
+    p.C = tokens; p.ldc = E; p.alpha = 1.f;
+    return tc_gemm(c.m.h, m_pt, p, 1, E <= 64 ? 64 : 128, st);
 }

@@ -53,18 +53,37 @@ class SurgeryViT:
         self.embed = self.W["proj"].shape[1]
         self.grid0 = int(round((self.W["positional_embedding"].shape[0] - 1) ** 0.5))
         self._blocks = (_lib.VitLayer * L)()
+        self.Ws = {}   # split-fp16 weight copies: the tcgen05 GEMM engine's operand format
         for i in range(L):
             for f, name in _BLOCK_FIELDS:
                 setattr(self._blocks[i], f, self.W["blocks.%d.%s" % (i, name)].data_ptr())
+            for f, name in (("in_ws", "in_proj_weight"), ("out_ws", "out_proj.weight"), ("fc_ws", "c_fc.weight"),
+                            ("proj_ws", "c_proj.weight")):
+                setattr(self._blocks[i], f, self._split("blocks.%d.%s" % (i, name)).data_ptr())
         w = _lib.VitWeights()
         w.layers, w.width, w.heads, w.patch, w.embed, w.grid0, w.n_surgery = L, self.width, H, P, self.embed, self.grid0, n_surgery
         for f, name in (("conv1", "conv1.weight"), ("cls", "class_embedding"), ("pos", "positional_embedding"),
                         ("ln_pre_w", "ln_pre.weight"), ("ln_pre_b", "ln_pre.bias"), ("ln_post_w", "ln_post.weight"),
                         ("ln_post_b", "ln_post.bias"), ("proj", "proj")):
             setattr(w, f, self.W[name].data_ptr())
+        self.W["conv1.flat"] = self.W["conv1.weight"].reshape(self.width, -1).contiguous()
+        self.W["proj.t"] = self.W["proj"].t().contiguous()
+        w.conv1_s = self._split("conv1.flat").data_ptr()
+        w.proj_t_s = self._split("proj.t").data_ptr()
         w.blocks = ctypes.cast(self._blocks, ctypes.POINTER(_lib.VitLayer))
         self._w = w
         self._ws = None
+
+    def _split(self, name):
+        """fp32 weight [out, in] -> split fp16 [out, 2*round_up(in, 64)] (hi | lo) on the device."""
+        x = self.W[name]
+        rows, cols = x.shape
+        kp = (cols + 63) // 64 * 64
+        out = torch.empty((rows, 2 * kp), dtype=torch.float16, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("excel_split_f16", _lib.ptr(x), x.stride(0), rows, cols, kp, _lib.ptr(out), _lib.stream())
+        self.Ws[name] = out
+        return out
 
     @classmethod
     def from_visual(cls, visual, n_surgery=5, device="cuda"):
@@ -85,7 +104,7 @@ class SurgeryViT:
         nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
         if self._ws is None or self._ws.numel() * 4 < nbytes:
             self._ws = None
-            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)   # 512 B-aligned by the allocator
         tokens = torch.empty((B, N, self.embed), dtype=torch.float32, device=self.device)
         attn = torch.empty((self.layers, B, N, N), dtype=torch.float32, device=self.device)
         feats = torch.empty((self.layers, B, N, self.width), dtype=torch.float32, device=self.device)

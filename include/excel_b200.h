@@ -109,6 +109,8 @@ int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E
  * :396-405); out_w/out_b = attn.out_proj (or Attention.proj). */
 typedef struct {
     const float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
+    /* split-fp16 copies of the four weight matrices (excel_split_f16 at load time): [out, 2*in] halves, hi | lo */
+    const void *in_ws, *out_ws, *fc_ws, *proj_ws;
 } ExcelVitLayer;
 
 /* VisionTransformer (clip/clip_surgery_model.py:374-448).  conv1 [width, 3*patch*patch]; cls [width];
@@ -117,10 +119,15 @@ typedef struct {
 typedef struct {
     int layers, width, heads, patch, embed, grid0, n_surgery;
     const float *conv1, *cls, *pos, *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b, *proj;
+    const void *conv1_s, *proj_t_s;   /* split-fp16 conv1 [width, 2*Kp] and proj^T [embed, 2*width] */
     const ExcelVitLayer* blocks;
 } ExcelVitWeights;
 
 int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int heads);
+
+/* fp32 [rows, cols] (row pitch ldx) -> split fp16 [rows, 2*Kp] (hi | lo, zero padded), Kp % 64 == 0: the
+ * operand format of the tcgen05 GEMM engine (x = hi + lo keeps 22 significant bits). */
+int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, void* out, void* stream);
 
 /* VisionTransformer.forward + Transformer.forward (clip/clip_surgery_model.py:418-448, 346-371) as called by
  * clip.generate_clip_fts (clip/clip.py:348-358), for img [B,3,S,S] (element strides b, c, y; x contiguous).
@@ -145,6 +152,12 @@ int excel_confusion_hist(const int64_t* label_true, const int64_t* label_pred, i
 int excel_sgemm(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
                 int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB, int64_t strideC,
                 float alpha, int b_is_nk, int act, void* stream);
+
+/* The same contraction on the tcgen05 tensor cores: C = act(alpha * A B^T + bias) + residual for fp32
+ * row-major A [M,K] (lda) and B [N,K] (ldb, the nn.Linear weight layout).  Operands are split into fp16
+ * hi/lo pairs (fp32-quality products, three MMA passes); ws >= 4*(M+N)*round_up(K,64) bytes. */
+int excel_gemm_tc(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
+                  int64_t lda, int64_t ldb, int64_t ldc, float alpha, int act, void* ws, int64_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }
