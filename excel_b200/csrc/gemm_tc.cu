@@ -31,7 +31,8 @@ constexpr int kBM = 128, kBK = 64, kTcStages = 3;
 constexpr uint32_t kTileBytes = kBM * kBK * 2;        // one 128-row x 64-k fp16 tile: 16 KB
 constexpr uint32_t kStageBytes = 4 * kTileBytes;      // A_hi, A_lo, B_hi, B_lo (B tiles use BN*128 B of their slot)
 constexpr int kTcThreads = 192;
-constexpr size_t kTcSmem = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kEpiBytes = 2 * 16384;             // epilogue staging: two 128-row x 128 B blocks (TMA store sources)
+constexpr size_t kTcSmem = kTcStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 // ---- tcgen05 / TMEM PTX -------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -80,148 +81,271 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 
-template <int kBN>
+// Persistent kernel: one CTA per SM walks the output tiles t = blockIdx.x + i*gridDim.x (n fastest, so
+// neighbouring CTAs share A rows in L2).  Two TMEM accumulators (2 x kBN columns) let the epilogue of tile i
+// overlap the main loop of tile i+1; the operand ring keeps running across tile boundaries.
+// TMA_EPI: the output leaves through TMA stores (fp32 tile: 4D map tmC; split-fp16: 3D map tmS) -- the epilogue
+// threads only move TMEM -> registers -> swizzled shared memory; otherwise (oddly pitched outputs) they store
+// to global themselves.
+template <int kBN, bool TMA_EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS, const TcParams p,
+               int tiles_n, int tiles_m, int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024 B alignment
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kTcStages * kStageBytes);
+    float* stage = reinterpret_cast<float*>(tiles + kTcStages * kStageBytes);      // epilogue staging, 128 x 36 floats
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kTcStages * kStageBytes + kEpiBytes);
     uint64_t* empty_bar = full_bar + kTcStages;
-    uint64_t* accum_bar = empty_bar + kTcStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* acc_full = empty_bar + kTcStages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * kBN, m0 = blockIdx.y * kBM;
-    const int z1 = blockIdx.z / p.nb2, z2 = blockIdx.z % p.nb2;
     constexpr uint32_t kIdesc = make_idesc(kBN);
     constexpr uint32_t kTxBytes = 2 * kTileBytes + 2 * kBN * kBK * 2;
-    const int a_row = p.a_row0 + z1 * p.a_row1 + z2 * p.a_row2 + m0, a_col = p.a_col0 + z1 * p.a_col1 + z2 * p.a_col2;
-    const int b_row = p.b_row0 + z1 * p.b_row1 + z2 * p.b_row2 + n0, b_col = p.b_col0 + z1 * p.b_col1 + z2 * p.b_col2;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kBN);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * kBN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    auto decode = [&](int t, int& m0, int& n0, int& z1, int& z2) {
+        const int nt = t % tiles_n, r = t / tiles_n;
+        const int mt = r % tiles_m, z = r / tiles_m;
+        m0 = mt * kBM; n0 = nt * kBN; z1 = z / p.nb2; z2 = z % p.nb2;
+    };
+
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-                const int s = kb % kTcStages;
-                mbar_wait(&empty_bar[s], ((kb / kTcStages) & 1) ^ 1);
-                uint8_t* st = tiles + s * kStageBytes;
-                mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
-                tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
-                tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
-                tma_load_2d(st + 2 * kTileBytes, &tmB, &full_bar[s], b_col + kb * kBK, b_row);
-                tma_load_2d(st + 3 * kTileBytes, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row);
+            int it = 0;  // running k-block counter across tiles
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m0, n0, z1, z2;
+                decode(t, m0, n0, z1, z2);
+                const int a_row = p.a_row0 + z1 * p.a_row1 + z2 * p.a_row2 + m0, a_col = p.a_col0 + z1 * p.a_col1 + z2 * p.a_col2;
+                const int b_row = p.b_row0 + z1 * p.b_row1 + z2 * p.b_row2 + n0, b_col = p.b_col0 + z1 * p.b_col1 + z2 * p.b_col2;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % kTcStages;
+                    mbar_wait(&empty_bar[s], ((it / kTcStages) & 1) ^ 1);
+                    uint8_t* st = tiles + s * kStageBytes;
+                    mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
+                    tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
+                    tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
+                    tma_load_2d(st + 2 * kTileBytes, &tmB, &full_bar[s], b_col + kb * kBK, b_row);
+                    tma_load_2d(st + 3 * kTileBytes, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-                const int s = kb % kTcStages;
-                mbar_wait(&full_bar[s], (kb / kTcStages) & 1);
+            int it = 0, i = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+                const int buf = i & 1;
+                mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t st = smem_u32(tiles + s * kStageBytes);
-                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * kBN);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                    const int s = it % kTcStages;
+                    mbar_wait(&full_bar[s], (it / kTcStages) & 1);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(tiles + s * kStageBytes);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
 #pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 fp16 = 32 B further along K inside the swizzle atom
-                    umma_f16(tmem_base, a_hi + adv, b_lo + adv, kIdesc, (kb | k) != 0);
-                    umma_f16(tmem_base, a_lo + adv, b_hi + adv, kIdesc, 1);
-                    umma_f16(tmem_base, a_hi + adv, b_hi + adv, kIdesc, 1);
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 fp16 = 32 B further along K inside the swizzle atom
+                        umma_f16(tacc, a_hi + adv, b_lo + adv, kIdesc, (kb | k) != 0);
+                        umma_f16(tacc, a_lo + adv, b_hi + adv, kIdesc, 1);
+                        umma_f16(tacc, a_hi + adv, b_hi + adv, kIdesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);  // stage s may be refilled once these MMAs have read it
                 }
-                umma_commit(&empty_bar[s]);  // stage s may be refilled once these MMAs have read it
+                umma_commit(&acc_full[buf]);     // accumulator complete
             }
-            umma_commit(accum_bar);          // accumulator complete
         }
     } else {
-        // ---- epilogue: warp w owns TMEM lanes 32*(w%4)..+31 == output rows m0 + 32*(w%4) + lane
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        // ---- epilogue (warps 2..5).  Warp w owns TMEM lanes 32*(w%4)..+31 == tile rows 32*(w%4)+lane.
         const int lg = warp & 3;
-        const int m = m0 + lg * 32 + lane;
-        const bool row_ok = m < p.M;
-        const int64_t coff = (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2 + (int64_t)m * p.ldc;
-        const int64_t soff = (int64_t)z1 * p.cs1 + (int64_t)z2 * p.cs2 + (int64_t)m * p.lds;
+        const int trow = lg * 32 + lane;
+        const float alpha = p.alpha;
+        const int act = p.act;
+        const float* bias = p.bias;
+        int i = 0;
+        if constexpr (TMA_EPI) {
+            // Per 32-column chunk each thread pulls its row slice out of TMEM, applies alpha / bias / QuickGELU /
+            // residual and writes it into a swizzled staging buffer (two, alternating); one elected thread then
+            // hands the 128 x 32 block to the TMA store engine, which also clips rows >= M and columns >= N.
+            uint8_t* ebuf = reinterpret_cast<uint8_t*>(stage);
+            const bool leader = threadIdx.x == 64;
+            int ck = 0;  // running chunk counter -> staging buffer parity
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+                int m0, n0, z1, z2;
+                decode(t, m0, n0, z1, z2);
+                const int buf = i & 1;
+                mbar_wait(&acc_full[buf], (i >> 1) & 1);
+                tc_fence_after();
+                const float* resrow = p.residual ? p.residual + (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2 + (int64_t)(m0 + trow) * p.ldc : nullptr;
+                const bool row_ok = m0 + trow < p.M;
 #pragma unroll 1
-        for (int c = 0; c < kBN / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
-            const int nb = n0 + c * 32;
-            if (!row_ok || nb >= p.N) continue;
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float t = p.alpha * __uint_as_float(r[j]);
-                if (p.bias && nb + j < p.N) t += __ldg(p.bias + nb + j);
-                if (p.act == 1) t = t * (1.f / (1.f + expf(-1.702f * t)));  // QuickGELU
-                v[j] = t;
-            }
-            if (p.C) {
-                float* dst = p.C + coff + nb;
-                const float* res = p.residual ? p.residual + coff + nb : nullptr;
-                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
-                    (!res || (reinterpret_cast<uintptr_t>(res) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (res) {
-                            const float4 q = *reinterpret_cast<const float4*>(res + j);
-                            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-                        }
-                        *reinterpret_cast<float4*>(dst + j) = o;
+                for (int c = 0; c < kBN / 32; ++c, ++ck) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * kBN + c * 32), r);
+                    if (c == kBN / 32 - 1) {  // all of this thread's TMEM reads for the tile are done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
                     }
-                } else {
+                    const int nb = n0 + c * 32;
+                    if (nb >= p.N) continue;   // (uniform) nothing to store for this chunk
+                    uint8_t* sb = ebuf + (ck & 1) * 16384;
+                    if (leader) tma_store_wait_read<1>();  // the store that last read this buffer has drained
+                    bar_sync(1, 128);
+                    float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < p.N) dst[j] = v[j] + (res ? res[j] : 0.f);
+                    for (int j = 0; j < 32; ++j) {
+                        float x = alpha * __uint_as_float(r[j]);
+                        if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
+                        if (act == 1) x = x * (1.f / (1.f + expf(-1.702f * x)));  // QuickGELU
+                        v[j] = x;
+                    }
+                    if (p.C) {
+                        if (resrow && row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (nb + j + 3 < p.N) {
+                                    const float4 q = *reinterpret_cast<const float4*>(resrow + nb + j);
+                                    v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (nb + j + e < p.N) v[j + e] += resrow[nb + j + e];
+                                }
+                            }
+                        }
+                        // fp32 tile [128][32]: 128 B rows, SWIZZLE_128B (16 B chunk index ^= row % 8): conflict-free
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(sb + trow * 128 + ((j ^ (trow & 7)) << 4)) =
+                                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    } else {
+                        // split fp16 tiles hi | lo, [128][32] halves each: 64 B rows, SWIZZLE_64B (chunk ^= (row/2) % 4)
+                        uint8_t* sh = sb;
+                        uint8_t* sl = sb + 8192;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __align__(16) __half h[8], l[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                h[e] = __float2half_rn(v[8 * j + e]);
+                                l[e] = __float2half_rn(v[8 * j + e] - __half2float(h[e]));
+                            }
+                            const int off = trow * 64 + ((j ^ ((trow >> 1) & 3)) << 4);
+                            *reinterpret_cast<uint4*>(sh + off) = *reinterpret_cast<const uint4*>(h);
+                            *reinterpret_cast<uint4*>(sl + off) = *reinterpret_cast<const uint4*>(l);
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    bar_sync(1, 128);
+                    if (leader) {
+                        if (p.C) {
+                            tma_store_4d(&tmC, sb, nb, m0, z2, z1);
+                        } else {
+                            const int col = z2 * (int)p.cs2 + nb;
+                            tma_store_3d(&tmS, sb, col, m0, z1);
+                            tma_store_3d(&tmS, sb + 8192, col + p.cs_lo_off, m0, z1);
+                        }
+                        tma_store_commit();
+                    }
                 }
             }
-            if (p.Cs) {  // split-fp16 copy of the result (operand of the next GEMM); no residual on this path
-                __half* hi = p.Cs + soff + nb;
-                __half* lo = hi + p.cs_lo_off;
-                if (nb + 32 <= p.N && ((reinterpret_cast<uintptr_t>(hi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(lo) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __align__(16) __half h[8], l[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            h[e] = __float2half_rn(v[j + e]);
-                            l[e] = __float2half_rn(v[j + e] - __half2float(h[e]));
-                        }
-                        *reinterpret_cast<uint4*>(hi + j) = *reinterpret_cast<const uint4*>(h);
-                        *reinterpret_cast<uint4*>(lo + j) = *reinterpret_cast<const uint4*>(l);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (nb + j < p.N) {
-                            const __half h = __float2half_rn(v[j]);
-                            hi[j] = h;
-                            lo[j] = __float2half_rn(v[j] - __half2float(h));
-                        }
+            if (leader) tma_store_wait_read<0>();
+        } else {
+        // Fallback for outputs TMA cannot address (row pitch not a multiple of 16 B): stage 128 x 32 blocks in shared
+        // memory (pitch 36 floats) and stream them out with 8 lanes per row (128 B segments).
+        constexpr int kPitch = 36;
+        const int ew = warp - 2, sub = lane >> 3, c4 = (lane & 7) * 4;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+            int m0, n0, z1, z2;
+            decode(t, m0, n0, z1, z2);
+            const int buf = i & 1;
+            mbar_wait(&acc_full[buf], (i >> 1) & 1);
+            tc_fence_after();
+            const int64_t zoffc = (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2;
+            const int64_t zoffs = (int64_t)z1 * p.cs1 + (int64_t)z2 * p.cs2;
+#pragma unroll 1
+            for (int c = 0; c < kBN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * kBN + c * 32), r);
+                if (c == kBN / 32 - 1) {  // all of this thread's TMEM reads for the tile are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
+                const int nb = n0 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float x = alpha * __uint_as_float(r[j + e]);
+                        if (bias && nb + j + e < p.N) x += __ldg(bias + nb + j + e);
+                        if (act == 1) x = x * (1.f / (1.f + expf(-1.702f * x)));  // QuickGELU
+                        v[e] = x;
+                    }
+                    *reinterpret_cast<float4*>(stage + trow * kPitch + j) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                bar_sync(1, 128);
+                const int ncols = min(32, p.N - nb);
+                if (ncols > 0) {
+#pragma unroll 1
+                    for (int rr = ew * 4 + sub; rr < kBM; rr += 16) {
+                        const int m = m0 + rr;
+                        if (m >= p.M) break;
+                        const float* srow = stage + rr * kPitch + c4;
+                        if (p.C) {
+                            float* dst = p.C + zoffc + (int64_t)m * p.ldc + nb + c4;
+                            const float* res = p.residual ? p.residual + zoffc + (int64_t)m * p.ldc + nb + c4 : nullptr;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c4 + e < ncols) dst[e] = srow[e] + (res ? res[e] : 0.f);
+                        }
+                        if (p.Cs) {  // split-fp16 copy (operand of the next GEMM); no residual on this path
+                            __half* hi = p.Cs + zoffs + (int64_t)m * p.lds + nb + c4;
+                            __half* lo = hi + p.cs_lo_off;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (c4 + e < ncols) {
+                                    const __half h = __float2half_rn(srow[e]);
+                                    hi[e] = h;
+                                    lo[e] = __float2half_rn(srow[e] - __half2float(h));
+                                }
+                        }
+                    }
+                }
+                bar_sync(1, 128);  // staging buffer is reused by the next chunk
             }
         }
-        tc_fence_before();
+        }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kBN);
+        tmem_dealloc(tmem_base, 2 * kBN);
     }
 }
 
@@ -248,16 +372,53 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
         attr_set = true;
     }
-    XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1, "tc_gemm: bad shape M=%d N=%d kblocks=%d", p.M, p.N, p.kblocks);
+    XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1 && batch % p.nb2 == 0,
+               "tc_gemm: bad shape M=%d N=%d kblocks=%d batch=%d", p.M, p.N, p.kblocks, batch);
     XL_REQUIRE(bn == 64 || bn == 128, "tc_gemm: tile N must be 64 or 128 (the B tensor map's box must match)");
-    XL_REQUIRE(batch <= 65535 && ceil_div(p.M, kBM) <= 65535, "tc_gemm: grid too large");
-    dim3 grid(ceil_div(p.N, bn), ceil_div(p.M, kBM), batch);
-    if (bn == 128) gemm_tc_kernel<128><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, p);
-    else gemm_tc_kernel<64><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, p);
+    XL_REQUIRE((p.C != nullptr) != (p.Cs != nullptr), "tc_gemm: exactly one of the fp32 / split-fp16 outputs");
+    const int tiles_n = ceil_div(p.N, bn), tiles_m = ceil_div(p.M, kBM);
+    const int64_t total = (int64_t)tiles_n * tiles_m * batch;
+    XL_REQUIRE(total < (1ll << 31), "tc_gemm: too many tiles");
+    const int grid = (int)(total < kNumSMs ? total : kNumSMs);  // persistent: one CTA per SM
+    const int nb1 = batch / p.nb2;
+    // output through TMA stores when the layout satisfies the tensor-map rules (16 B-aligned base and strides)
+    CUtensorMap tmC = tmA, tmS = tmA;  // placeholders when unused
+    bool tma_epi = false;
+    if (p.C) {
+        const bool ok = (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && p.ldc % 4 == 0 && p.c1 % 4 == 0 && p.c2 % 4 == 0 &&
+                        (!p.residual || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                        (nb1 == 1 || p.c1 > 0) && (p.nb2 == 1 || p.c2 > 0);
+        if (ok) {
+            const uint64_t dims[4] = {(uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.nb2, (uint64_t)nb1};
+            const uint64_t strides[3] = {(uint64_t)p.ldc * 4, (uint64_t)(p.nb2 > 1 ? p.c2 : p.ldc * (int64_t)p.M) * 4,
+                                         (uint64_t)(nb1 > 1 ? p.c1 : p.ldc * (int64_t)p.M * p.nb2) * 4};
+            const uint32_t box[4] = {32, kBM, 1, 1};
+            if (int e = encode_tensor_map(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.C, dims, strides, box,
+                                          CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+            tma_epi = true;
+        }
+    } else {
+        const bool ok = (reinterpret_cast<uintptr_t>(p.Cs) & 15) == 0 && p.lds % 8 == 0 && p.cs1 % 8 == 0 && p.N % 32 == 0 &&
+                        p.cs_lo_off % 8 == 0 && p.cs2 % 8 == 0 && (nb1 == 1 || p.cs1 > 0);
+        if (ok) {
+            const uint64_t dims[3] = {(uint64_t)p.lds, (uint64_t)p.M, (uint64_t)nb1};
+            const uint64_t strides[2] = {(uint64_t)p.lds * 2, (uint64_t)(nb1 > 1 ? p.cs1 : p.lds * (int64_t)p.M) * 2};
+            const uint32_t box[3] = {32, kBM, 1};
+            if (int e = encode_tensor_map(&tmS, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, p.Cs, dims, strides, box,
+                                          CU_TENSOR_MAP_SWIZZLE_64B)) return e;
+            tma_epi = true;
+        }
+    }
+#define XL_TC_LAUNCH(BN_, EPI_) gemm_tc_kernel<BN_, EPI_><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
+    if (bn == 128) { if (tma_epi) XL_TC_LAUNCH(128, true); else XL_TC_LAUNCH(128, false); }
+    else { if (tma_epi) XL_TC_LAUNCH(64, true); else XL_TC_LAUNCH(64, false); }
+#undef XL_TC_LAUNCH
     return check_launch("gemm_tc_kernel");
 }
 

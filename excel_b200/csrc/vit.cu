@@ -113,29 +113,61 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
-// ---- row softmax in place (rows of length n) + split-fp16 copy P_s [rows, 2*np] (zero padded) -----------
-__global__ void __launch_bounds__(128)
-softmax_rows_kernel(float* __restrict__ S, int n, __half* __restrict__ Ps, int np) {
-    __shared__ float red[32];
-    float* row = S + (int64_t)blockIdx.x * n;
-    float mx = -INFINITY;
-    for (int j = threadIdx.x; j < n; j += 128) mx = fmaxf(mx, row[j]);
-    mx = block_reduce(mx, red, OpMax(), -INFINITY);
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < n; j += 128) {
-        const float e = expf(row[j] - mx);
-        row[j] = e;
-        sum += e;
-    }
-    sum = block_reduce(sum, red, OpSum(), 0.f);
-    __half* ph = Ps + (int64_t)blockIdx.x * 2 * np;
-    for (int j = threadIdx.x; j < np; j += 128) {
-        float v = 0.f;
-        if (j < n) {
-            v = row[j] / sum;
-            row[j] = v;
+// ---- softmax over keys for ALL heads of one query row + head reduction ----------------------------------
+// One block per (b, query row n).  For every head h: P = softmax(S[b,h,n,:]) is written as the split-fp16
+// operand of the P V GEMM (scaled by 2^10, zero padded to np keys) and summed into the head-reduced row
+// out[b,n,:] (+)= coef * sum_h P -- the attention map the encoder must return (head MEAN before the surgery,
+// head SUM in the surgery blocks, clip_surgery_model.py:154,360) or the new-path map (:125,146).
+// S rows have pitch np (16 B aligned); scores were scaled by the GEMM.
+// One WARP per (b, n): the row lives in registers (np/32 values per lane), reductions are shuffles, no block barrier.
+constexpr int kSmMaxPer = 40;  // np <= 1280 keys per warp-resident row
+
+template <int PER>
+__global__ void __launch_bounds__(256)
+softmax_heads_kernel(const float* __restrict__ S, int N, int np, int H, int B, __half* __restrict__ Ps, float* __restrict__ out,
+                     float coef, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t bn = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (bn >= (int64_t)B * N) return;
+    const int b = (int)(bn / N), n = (int)(bn - (int64_t)b * N);
+    float acc[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) acc[i] = 0.f;
+    for (int h = 0; h < H; ++h) {
+        const int64_t r = ((int64_t)b * H + h) * N + n;
+        const float* row = S + r * np;
+        float v[PER];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int j = lane + i * 32;
+            v[i] = j < N ? __ldcs(row + j) : -INFINITY;
+            mx = fmaxf(mx, v[i]);
         }
-        split_store(ph + j, ph + np + j, v * kProbScale);
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            v[i] = expf(v[i] - mx);  // exp(-inf) = 0 for the padding
+            sum += v[i];
+        }
+        sum = warp_sum(sum);
+        __half* ph = Ps + r * 2 * np;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int j = lane + i * 32;
+            if (j < np) {
+                const float pr = v[i] / sum;
+                acc[i] += pr;
+                split_store(ph + j, ph + np + j, pr * kProbScale);
+            }
+        }
+    }
+    float* o = out + ((int64_t)b * N + n) * N;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int j = lane + i * 32;
+        if (j < N) o[j] = accumulate ? o[j] + coef * acc[i] : coef * acc[i];
     }
 }
 
@@ -165,20 +197,6 @@ vt_kernel(const __half* __restrict__ qkv, int N, int D, int np, __half* __restri
     }
 }
 
-// ---- out[b,i,j] (+)= coef * sum_h P[b,h,i,j] ------------------------------------------------------------
-__global__ void head_reduce_kernel(const float* __restrict__ P, float* __restrict__ out, int H, int64_t nn, float coef,
-                                   int accumulate) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (i >= nn) return;
-    const float* p = P + (int64_t)b * H * nn + i;
-    float s = 0.f;
-    for (int h = 0; h < H; ++h) s += p[(int64_t)h * nn];
-    s *= coef;
-    float* o = out + (int64_t)b * nn + i;
-    *o = accumulate ? *o + s : s;
-}
-
 __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t stride_b, int D) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (d < D) dst[(int64_t)b * stride_b + d] = src[(int64_t)b * stride_b + d];
@@ -195,7 +213,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
     size_t t = 0;
     t += align256((size_t)N * D * 4);                 // pos
-    t += align256((size_t)B * H * N * N * 4);         // S
+    t += align256((size_t)B * H * N * np * 4);        // S (row pitch np)
     t += align256((size_t)B * N * N * 4);             // pnew
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
@@ -235,16 +253,26 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     return tc_gemm(ma, mw, p, 1, 128, c.st);
 }
 
-// S[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s; also P_s
-static int scores(const Ctx& c, int xo, int yo, float scale) {
+// P[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s -> P_s, and the
+// head-reduced map out[b] (+)= coef * sum_h P[b,h]
+static int scores(const Ctx& c, int xo, int yo, float scale, float* out, float coef, int accumulate) {
     TcParams p = {};
     p.M = c.N; p.N = c.N; p.kblocks = c.dh / 64; p.a_lo_off = 3 * c.D; p.b_lo_off = 3 * c.D; p.nb2 = c.H;
     p.a_row1 = c.N; p.a_col0 = xo; p.a_col2 = c.dh;
     p.b_row1 = c.N; p.b_col0 = yo; p.b_col2 = c.dh;
-    p.C = c.w.S; p.ldc = c.N; p.c1 = (int64_t)c.H * c.N * c.N; p.c2 = (int64_t)c.N * c.N; p.alpha = scale;
+    p.C = c.w.S; p.ldc = c.np; p.c1 = (int64_t)c.H * c.N * c.np; p.c2 = (int64_t)c.N * c.np; p.alpha = scale;
     if (int e = tc_gemm(c.m.qkv_a, c.m.qkv_b, p, c.B * c.H, 128, c.st)) return e;
-    softmax_rows_kernel<<<(unsigned)((int64_t)c.B * c.H * c.N), 128, 0, c.st>>>(c.w.S, c.N, c.w.P, c.np);
-    return check_launch("softmax_rows_kernel");
+    XL_REQUIRE(c.np <= 32 * kSmMaxPer, "vit_forward: %d tokens exceed the softmax kernel's row capacity (%d)", c.N, 32 * kSmMaxPer);
+    const unsigned grid = (unsigned)ceil_div64(c.BN, 8);
+    const int per = c.np / 32;
+#define XL_SM_LAUNCH(PER_) softmax_heads_kernel<PER_><<<grid, 256, 0, c.st>>>(c.w.S, c.N, c.np, c.H, c.B, c.w.P, out, coef, accumulate)
+    if (per <= 8) XL_SM_LAUNCH(8);
+    else if (per <= 16) XL_SM_LAUNCH(16);
+    else if (per <= 26) XL_SM_LAUNCH(26);
+    else if (per <= 34) XL_SM_LAUNCH(34);
+    else XL_SM_LAUNCH(40);
+#undef XL_SM_LAUNCH
+    return check_launch("softmax_heads_kernel");
 }
 
 // o_s[b, :, h*dh..] = P[b,h] V[b,h]   (split output feeding the out projection)
@@ -256,13 +284,6 @@ static int attn_v(const Ctx& c) {
     p.alpha = 1.f / kProbScale;
     p.Cs = c.w.o; p.lds = 2 * c.D; p.cs1 = (int64_t)c.N * 2 * c.D; p.cs2 = c.dh; p.cs_lo_off = c.D;
     return tc_gemm(c.m.P, c.m.vt64, p, c.B * c.H, 64, c.st);
-}
-
-static int head_reduce(const Ctx& c, float* out, float coef, int accumulate) {
-    const int64_t nn = (int64_t)c.N * c.N;
-    dim3 grid((unsigned)ceil_div64(nn, 256), c.B);
-    head_reduce_kernel<<<grid, 256, 0, c.st>>>(c.w.S, out, c.H, nn, coef, accumulate);
-    return check_launch("head_reduce_kernel");
 }
 
 // ln_1 -> in_proj -> split qkv, V^T
@@ -323,7 +344,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
         auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
         c.w.pos = (float*)take((size_t)N * D * 4);
-        c.w.S = (float*)take((size_t)B * H * N * N * 4);
+        c.w.S = (float*)take((size_t)B * H * N * np * 4);
         c.w.pnew = (float*)take((size_t)B * N * N * 4);
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
@@ -393,8 +414,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
             if (int e = qkv_stage(c, x, Lw, m_in)) return e;
-            if (int e = scores(c, 0, D, scale)) return e;
-            if (int e = head_reduce(c, attn_l, 1.f / H, 0)) return e;  // need_weights: head mean
+            if (int e = scores(c, 0, D, scale, attn_l, 1.f / H, 0)) return e;  // need_weights: head mean
             if (int e = attn_v(c)) return e;
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
@@ -404,10 +424,8 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
             if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
-            for (int t = 0; t < 3; ++t) {
-                if (int e = scores(c, t * D, t * D, scale)) return e;
-                if (int e = head_reduce(c, c.w.pnew, 1.f / 3.f, t > 0)) return e;
-            }
+            for (int t = 0; t < 3; ++t)
+                if (int e = scores(c, t * D, t * D, scale, c.w.pnew, 1.f / 3.f, t > 0)) return e;
             if (int e = split_f16(c.w.pnew, N, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
@@ -417,8 +435,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                 if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
-            if (int e = scores(c, 0, D, scale)) return e;
-            if (int e = head_reduce(c, attn_l, 1.f, 0)) return e;
+            if (int e = scores(c, 0, D, scale, attn_l, 1.f, 0)) return e;
             if (int e = attn_v(c)) return e;                                  // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
