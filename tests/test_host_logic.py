@@ -97,3 +97,34 @@ print('ok', r)
                           "127.0.0.1", "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_install_rebinds_reference_symbols():
+    """Drop-in mechanics (needs the reference tree: build container only)."""
+    import pytest
+    from oracle import ref_harness as H
+    if not H.available():
+        pytest.skip("reference tree not present (GPU box)")
+    H.load()
+    import importlib
+    from excel_b200 import install as inst, par, affutils
+    orig = inst.install()
+    try:
+        aff = importlib.import_module("utils.affutils")
+        assert importlib.import_module("utils.PAR").PAR is par.PAR
+        assert aff.refine_cams_with_bkg_weclip is affutils.refine_cams_with_bkg_weclip
+        ns = {}
+        exec("from utils.affutils import refine_cams_with_aff, refine_cams_with_bkg_weclip\nfrom utils.PAR import PAR\nimport clip", ns)
+        assert ns["PAR"] is par.PAR and ns["clip"].clip_feature_surgery.__module__ == "excel_b200.clip"
+        # a CPU tensor must not silently run the reference: the patched path refuses (no fallback)
+        with pytest.raises(RuntimeError):
+            ns["clip"].clip_feature_surgery(torch.zeros(1, 5, 8), torch.zeros(3, 8))
+    finally:
+        inst.uninstall(orig)
+    assert importlib.import_module("utils.PAR").PAR is not par.PAR
+
+
+def test_merge_flipped_maps_matches_oracle():
+    from excel_b200.camutils import merge_flipped_maps
+    x = torch.rand(4, 36, 20, generator=torch.Generator().manual_seed(0))
+    assert torch.allclose(merge_flipped_maps(x, 2, 6, 6), port.cure_attr_map_flip_post(x, 6), atol=1e-7)
