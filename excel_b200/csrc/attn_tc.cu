@@ -1,0 +1,276 @@
+// Attention probabilities on tcgen05 without materialising the scores (reference: nn.MultiheadAttention with
+// need_weights and the surgery Attention.forward, clip/clip_surgery_model.py:95-159,297-307).
+//
+// For X, Y in {q, k, v} the encoder needs  P[b,h] = softmax_j(scale * X_h Y_h^T)  twice over: as the operand of the
+// P V product (per head) and reduced over heads (the attention map the API returns / the new-path map).  The
+// N x N scores per head (857 MB per score set at 512^2 x 16) never leave the chip:
+//   MODE 0 (stats): per (b, h, 128-row block) walk the key blocks, S tile = X Y^T on the tensor cores (split-fp16,
+//           3 MMA passes) into TMEM; the epilogue warps keep a running row max / sum (exp2 domain) -> m, l [B,H,N].
+//   MODE 1 (probs): per (b, row block, key block) walk the HEADS: S tile again, p = exp2(s - m) / l exactly
+//           normalised; (a) written as the split-fp16 P operand through a TMA store, (b) summed over heads in
+//           registers and written once as coef * sum_h p (+ the previous content) -> out [B,N,N].
+// Skeleton = the persistent GEMM's (gemm_tc.cu): TMA producer warp, single-thread tcgen05.mma issuer, double-
+// buffered TMEM accumulators; 8 epilogue warps (two per TMEM lane group, each taking half of the 128 columns).
+#include <cuda_fp16.h>
+
+#include "attn_tc.cuh"
+#include "common.cuh"
+#include "excel_b200.h"
+#include "tc.cuh"
+
+namespace xl {
+
+constexpr int kABK = 64;                                  // head dim == one 64-wide k block
+constexpr int kAStages = 2;
+constexpr uint32_t kATile = 128 * kABK * 2;               // 16 KB: one 128-row fp16 operand tile
+constexpr uint32_t kAStage = 4 * kATile;                  // X_hi, X_lo, Y_hi, Y_lo
+constexpr uint32_t kAEpi = 4 * 16384;                     // 2 teams x 2 TMA-store staging buffers
+constexpr int kAThreads = 64 + 256;
+constexpr size_t kASmem = kAStages * kAStage + kAEpi + 2048 /*row stats exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr float kProbScaleA = 1024.f;                     // must match vit.cu: kProbScale
+
+template <int MODE>
+__global__ void __launch_bounds__(kAThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmP, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* ebuf = tiles + kAStages * kAStage;
+    float* xch = reinterpret_cast<float*>(ebuf + kAEpi);  // [2][128] (m, l) of the second column half
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ebuf + kAEpi + 2048);
+    uint64_t* empty_bar = full_bar + kAStages;
+    uint64_t* acc_full = empty_bar + kAStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nblk = (p.N + 127) / 128;                   // row blocks == key blocks
+    const int inner = MODE == 0 ? nblk : p.H;             // consecutive tiles of one work item
+    const int items = MODE == 0 ? p.B * p.H * nblk : p.B * nblk * nblk;
+    constexpr uint32_t kIdesc = make_idesc(128);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kAStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 8);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item -> (b, h, rb, kb); j = position inside the item
+    auto decode = [&](int item, int j, int& b, int& h, int& rb, int& kb) {
+        if (MODE == 0) {   // item = (b, h, rb), j = kb
+            rb = item % nblk; const int r = item / nblk; h = r % p.H; b = r / p.H; kb = j;
+        } else {           // item = (b, rb, kb), j = h
+            kb = item % nblk; const int r = item / nblk; rb = r % nblk; b = r / nblk; h = j;
+        }
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x)
+                for (int j = 0; j < inner; ++j, ++it) {
+                    int b, h, rb, kb;
+                    decode(item, j, b, h, rb, kb);
+                    const int s = it % kAStages;
+                    mbar_wait(&empty_bar[s], ((it / kAStages) & 1) ^ 1);
+                    uint8_t* st = tiles + s * kAStage;
+                    mbar_arrive_expect_tx(&full_bar[s], kAStage);
+                    const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
+                    tma_load_2d(st, &tmQ, &full_bar[s], p.xo + h * kABK, xr);
+                    tma_load_2d(st + kATile, &tmQ, &full_bar[s], p.xo + p.lo_off + h * kABK, xr);
+                    tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], p.yo + h * kABK, yr);
+                    tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], p.yo + p.lo_off + h * kABK, yr);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x)
+                for (int j = 0; j < inner; ++j, ++it) {
+                    const int buf = it & 1, s = it % kAStages;
+                    mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                    mbar_wait(&full_bar[s], (it / kAStages) & 1);
+                    tc_fence_after();
+                    const uint32_t tacc = tmem_base + (uint32_t)(buf * 128);
+                    const uint32_t st = smem_u32(tiles + s * kAStage);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kATile);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * kATile), b_lo = umma_desc_sw128(st + 3 * kATile);
+#pragma unroll
+                    for (int k = 0; k < kABK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                        umma_f16(tacc, a_hi + adv, b_lo + adv, kIdesc, k != 0);
+                        umma_f16(tacc, a_lo + adv, b_hi + adv, kIdesc, 1);
+                        umma_f16(tacc, a_hi + adv, b_hi + adv, kIdesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    umma_commit(&acc_full[buf]);
+                }
+        }
+    } else {
+        // ---- epilogue: warp (lg, half): TMEM lanes 32*lg..+31 (rows), columns 64*half..+63 of every S tile
+        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;   // warps 2..5 -> half 0, 6..9 -> half 1 (lane group = warp % 4)
+        const int trow = lg * 32 + lane;
+        const int team_bar = 1 + half;
+        const bool leader = (ew & 3) == 0 && lane == 0;           // first warp of the team
+        uint8_t* tbuf = ebuf + half * 2 * 16384;
+        int it = 0, ck = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            int b, h, rb, kb;
+            decode(item, 0, b, h, rb, kb);
+            const int row = rb * 128 + trow;
+            const bool row_ok = row < p.N;
+            float m_run = -INFINITY, l_run = 0.f;                 // MODE 0
+            float acc[2][32];                                     // MODE 1: head-summed probabilities
+            if (MODE == 1) {
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[cc][e] = 0.f;
+            }
+            for (int j = 0; j < inner; ++j, ++it) {
+                decode(item, j, b, h, rb, kb);
+                const int buf = it & 1;
+                float m_row = 0.f, linv = 0.f;
+                if (MODE == 1 && row_ok) {
+                    const int64_t si = ((int64_t)b * p.H + h) * p.N + row;
+                    m_row = __ldg(p.m + si);
+                    linv = 1.f / __ldg(p.l + si);
+                }
+                mbar_wait(&acc_full[buf], (it >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = half * 2 + cc;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + c * 32), r);
+                    if (cc == 1) {  // this warp's TMEM reads of the tile are done
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+                    const int key0 = kb * 128 + c * 32;
+                    if (MODE == 0) {
+                        float s[32], cmax = -INFINITY;
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            s[e] = key0 + e < p.N ? p.alpha * __uint_as_float(r[e]) : -INFINITY;
+                            cmax = fmaxf(cmax, s[e]);
+                        }
+                        const float m_new = fmaxf(m_run, cmax);
+                        if (m_new > -INFINITY) {
+                            float sum = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) sum += exp2f(s[e] - m_new);
+                            l_run = l_run * exp2f(m_run - m_new) + sum;
+                            m_run = m_new;
+                        }
+                    } else {
+                        float pr[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            const float v = (row_ok && key0 + e < p.N) ? exp2f(p.alpha * __uint_as_float(r[e]) - m_row) * linv : 0.f;
+                            pr[e] = v;
+                            acc[cc][e] += v;
+                        }
+                        if (p.write_p && key0 < p.np) {  // (uniform) P operand tile: split fp16, scaled, via TMA store
+                            uint8_t* sb = tbuf + (ck & 1) * 16384;
+                            if (leader) tma_store_wait_read<1>();
+                            bar_sync(team_bar, 128);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                __align__(16) __half hh[8], ll[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const float v = pr[8 * q + e] * kProbScaleA;
+                                    hh[e] = __float2half_rn(v);
+                                    ll[e] = __float2half_rn(v - __half2float(hh[e]));
+                                }
+                                const int off = trow * 64 + ((q ^ ((trow >> 1) & 3)) << 4);   // SWIZZLE_64B
+                                *reinterpret_cast<uint4*>(sb + off) = *reinterpret_cast<const uint4*>(hh);
+                                *reinterpret_cast<uint4*>(sb + 8192 + off) = *reinterpret_cast<const uint4*>(ll);
+                            }
+                            fence_proxy_async_smem();
+                            bar_sync(team_bar, 128);
+                            if (leader) {
+                                tma_store_3d(&tmP, sb, key0, rb * 128, b * p.H + h);
+                                tma_store_3d(&tmP, sb + 8192, p.np + key0, rb * 128, b * p.H + h);
+                                tma_store_commit();
+                            }
+                            ++ck;
+                        }
+                    }
+                }
+            }
+            if (MODE == 0) {
+                // merge the two column halves of each row, write m, l
+                if (half == 1) { xch[trow] = m_run; xch[128 + trow] = l_run; }
+                bar_sync(3, 256);
+                if (half == 0 && row_ok) {
+                    const float m1 = xch[trow], l1 = xch[128 + trow];
+                    const float mf = fmaxf(m_run, m1);
+                    const float lf = l_run * exp2f(m_run - mf) + l1 * exp2f(m1 - mf);
+                    const int64_t si = ((int64_t)b * p.H + h) * p.N + row;
+                    p.m[si] = mf;
+                    p.l[si] = lf;
+                }
+                bar_sync(3, 256);
+            } else if (row_ok) {
+                // head-reduced map: out[b,row,key] (+)= coef * sum_h p ; each thread writes its own row segment
+                float* o = p.out + ((int64_t)b * p.N + row) * p.N;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int key0 = kb * 128 + (half * 2 + cc) * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (key0 + e < p.N) o[key0 + e] = p.accumulate ? o[key0 + e] + p.coef * acc[cc][e] : p.coef * acc[cc][e];
+                }
+            }
+        }
+        if (MODE == 1 && leader) tma_store_wait_read<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
+        XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
+        attr_set = true;
+    }
+    XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N, "attn_scores: bad shape");
+    XL_REQUIRE(p.m && p.l && p.out, "attn_scores: missing buffers");
+    const int nblk = (p.N + 127) / 128;
+    CUtensorMap tmP = tmQ;
+    if (p.write_p) {
+        XL_REQUIRE(Ps != nullptr, "attn_scores: write_p without a P buffer");
+        const uint64_t dims[3] = {(uint64_t)2 * p.np, (uint64_t)p.N, (uint64_t)p.B * p.H};
+        const uint64_t strides[2] = {(uint64_t)2 * p.np * 2, (uint64_t)2 * p.np * 2 * p.N};
+        const uint32_t box[3] = {32, 128, 1};
+        if (int e = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, Ps, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return e;
+    }
+    const int items0 = p.B * p.H * nblk, items1 = p.B * nblk * nblk;
+    attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);
+    if (int e = check_launch("attn_tc_kernel<stats>")) return e;
+    attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);
+    return check_launch("attn_tc_kernel<probs>");
+}
+
+}  // namespace xl

@@ -1,0 +1,25 @@
+// Interface of the tcgen05 attention-probability kernels (attn_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xl {
+
+// P[b,h] = softmax_j(alpha' * X_h Y_h^T), X/Y = column blocks (xo, yo; 64 columns per head) of the split-fp16
+// qkv matrix [B*N, 2*lo_off] (hi | lo).  alpha = scale * log2(e) (the kernels work in the exp2 domain).
+struct AttnParams {
+    int B, H, N, np;        // np = round_up(N, 64): key pitch of the P operand
+    int xo, yo, lo_off;
+    float alpha;
+    float *m, *l;           // [B,H,N] row max (log2 domain) / row sum: written by the stats pass, read by the probs pass
+    float* out;             // [B,N,N]: (+)= coef * sum_h P[b,h]
+    float coef;
+    int accumulate;
+    int write_p;            // also emit the split-fp16 P operand [B*H*N, 2*np] (scaled by 2^10) for the P V GEMM
+};
+
+int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st);
+
+}  // namespace xl

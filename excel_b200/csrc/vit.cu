@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "excel_b200.h"
+#include "attn_tc.cuh"
 #include "gemm_tc.cuh"
 
 namespace xl {
@@ -113,64 +114,6 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
-// ---- softmax over keys for ALL heads of one query row + head reduction ----------------------------------
-// One block per (b, query row n).  For every head h: P = softmax(S[b,h,n,:]) is written as the split-fp16
-// operand of the P V GEMM (scaled by 2^10, zero padded to np keys) and summed into the head-reduced row
-// out[b,n,:] (+)= coef * sum_h P -- the attention map the encoder must return (head MEAN before the surgery,
-// head SUM in the surgery blocks, clip_surgery_model.py:154,360) or the new-path map (:125,146).
-// S rows have pitch np (16 B aligned); scores were scaled by the GEMM.
-// One WARP per (b, n): the row lives in registers (np/32 values per lane), reductions are shuffles, no block barrier.
-constexpr int kSmMaxPer = 40;  // np <= 1280 keys per warp-resident row
-
-template <int PER>
-__global__ void __launch_bounds__(256)
-softmax_heads_kernel(const float* __restrict__ S, int N, int np, int H, int B, __half* __restrict__ Ps, float* __restrict__ out,
-                     float coef, int accumulate) {
-    const int lane = threadIdx.x & 31;
-    const int64_t bn = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (bn >= (int64_t)B * N) return;
-    const int b = (int)(bn / N), n = (int)(bn - (int64_t)b * N);
-    float acc[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) acc[i] = 0.f;
-    for (int h = 0; h < H; ++h) {
-        const int64_t r = ((int64_t)b * H + h) * N + n;
-        const float* row = S + r * np;
-        float v[PER];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int j = lane + i * 32;
-            v[i] = j < N ? __ldcs(row + j) : -INFINITY;
-            mx = fmaxf(mx, v[i]);
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            v[i] = expf(v[i] - mx);  // exp(-inf) = 0 for the padding
-            sum += v[i];
-        }
-        sum = warp_sum(sum);
-        __half* ph = Ps + r * 2 * np;
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            const int j = lane + i * 32;
-            if (j < np) {
-                const float pr = v[i] / sum;
-                acc[i] += pr;
-                split_store(ph + j, ph + np + j, pr * kProbScale);
-            }
-        }
-    }
-    float* o = out + ((int64_t)b * N + n) * N;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int j = lane + i * 32;
-        if (j < N) o[j] = accumulate ? o[j] + coef * acc[i] : coef * acc[i];
-    }
-}
-
 // ---- V^T: vt[(b*D + c), token] from the V block of qkv_s, split halves, zero padded to np tokens -------------
 __global__ void __launch_bounds__(1024)
 vt_kernel(const __half* __restrict__ qkv, int N, int D, int np, __half* __restrict__ vt) {
@@ -203,7 +146,7 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 }
 
 struct Ws {  // workspace carve-up
-    float *pos, *S, *pnew, *mid, *x0;
+    float *pos, *m, *l, *pnew, *mid, *x0;
     __half *col, *h, *qkv, *vt, *P, *pn, *o, *o2, *u;
 };
 
@@ -213,7 +156,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
     size_t t = 0;
     t += align256((size_t)N * D * 4);                 // pos
-    t += align256((size_t)B * H * N * np * 4);        // S (row pitch np)
+    t += 2 * align256((size_t)B * H * N * 4);         // softmax row stats m, l
     t += align256((size_t)B * N * N * 4);             // pnew
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
@@ -253,26 +196,14 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     return tc_gemm(ma, mw, p, 1, 128, c.st);
 }
 
-// P[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s -> P_s, and the
-// head-reduced map out[b] (+)= coef * sum_h P[b,h]
-static int scores(const Ctx& c, int xo, int yo, float scale, float* out, float coef, int accumulate) {
-    TcParams p = {};
-    p.M = c.N; p.N = c.N; p.kblocks = c.dh / 64; p.a_lo_off = 3 * c.D; p.b_lo_off = 3 * c.D; p.nb2 = c.H;
-    p.a_row1 = c.N; p.a_col0 = xo; p.a_col2 = c.dh;
-    p.b_row1 = c.N; p.b_col0 = yo; p.b_col2 = c.dh;
-    p.C = c.w.S; p.ldc = c.np; p.c1 = (int64_t)c.H * c.N * c.np; p.c2 = (int64_t)c.N * c.np; p.alpha = scale;
-    if (int e = tc_gemm(c.m.qkv_a, c.m.qkv_b, p, c.B * c.H, 128, c.st)) return e;
-    XL_REQUIRE(c.np <= 32 * kSmMaxPer, "vit_forward: %d tokens exceed the softmax kernel's row capacity (%d)", c.N, 32 * kSmMaxPer);
-    const unsigned grid = (unsigned)ceil_div64(c.BN, 8);
-    const int per = c.np / 32;
-#define XL_SM_LAUNCH(PER_) softmax_heads_kernel<PER_><<<grid, 256, 0, c.st>>>(c.w.S, c.N, c.np, c.H, c.B, c.w.P, out, coef, accumulate)
-    if (per <= 8) XL_SM_LAUNCH(8);
-    else if (per <= 16) XL_SM_LAUNCH(16);
-    else if (per <= 26) XL_SM_LAUNCH(26);
-    else if (per <= 34) XL_SM_LAUNCH(34);
-    else XL_SM_LAUNCH(40);
-#undef XL_SM_LAUNCH
-    return check_launch("softmax_heads_kernel");
+// P[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s, never materialising the
+// scores (attn_tc.cu): the head-reduced map out[b] (+)= coef * sum_h P[b,h], and (write_p) the split P operand
+static int scores(const Ctx& c, int xo, int yo, float scale, float* out, float coef, int accumulate, int write_p) {
+    AttnParams p = {};
+    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.xo = xo; p.yo = yo; p.lo_off = 3 * c.D;
+    p.alpha = scale * 1.4426950408889634f;  // exp2 domain
+    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.accumulate = accumulate; p.write_p = write_p;
+    return attn_scores(c.m.qkv_a, p, write_p ? c.w.P : nullptr, c.st);
 }
 
 // o_s[b, :, h*dh..] = P[b,h] V[b,h]   (split output feeding the out projection)
@@ -344,7 +275,8 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
         auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
         c.w.pos = (float*)take((size_t)N * D * 4);
-        c.w.S = (float*)take((size_t)B * H * N * np * 4);
+        c.w.m = (float*)take((size_t)B * H * N * 4);
+        c.w.l = (float*)take((size_t)B * H * N * 4);
         c.w.pnew = (float*)take((size_t)B * N * N * 4);
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
@@ -414,7 +346,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
             if (int e = qkv_stage(c, x, Lw, m_in)) return e;
-            if (int e = scores(c, 0, D, scale, attn_l, 1.f / H, 0)) return e;  // need_weights: head mean
+            if (int e = scores(c, 0, D, scale, attn_l, 1.f / H, 0, 1)) return e;  // need_weights: head mean
             if (int e = attn_v(c)) return e;
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
@@ -425,7 +357,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
             for (int t = 0; t < 3; ++t)
-                if (int e = scores(c, t * D, t * D, scale, c.w.pnew, 1.f / 3.f, t > 0)) return e;
+                if (int e = scores(c, t * D, t * D, scale, c.w.pnew, 1.f / 3.f, t > 0, 0)) return e;
             if (int e = split_f16(c.w.pnew, N, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
@@ -435,7 +367,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                 if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
-            if (int e = scores(c, 0, D, scale, attn_l, 1.f, 0)) return e;
+            if (int e = scores(c, 0, D, scale, attn_l, 1.f, 0, 1)) return e;
             if (int e = attn_v(c)) return e;                                  // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
