@@ -44,8 +44,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.N + 127) / 128;                   // row blocks == key blocks
-    const int inner = MODE == 0 ? nblk : p.H;             // consecutive tiles of one work item
-    const int items = MODE == 0 ? p.B * p.H * nblk : p.B * nblk * nblk;
+    const int TH = p.ntypes * p.H;                        // (score set, head) pairs
+    const int inner = MODE == 0 ? nblk : TH;              // consecutive tiles of one work item
+    const int items = MODE == 0 ? p.B * TH * nblk : p.B * nblk * nblk;
     constexpr uint32_t kIdesc = make_idesc(128);
 
     if (threadIdx.x == 0) {
@@ -65,11 +66,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // work item -> (b, h, rb, kb); j = position inside the item
+    // work item -> (b, th, rb, kb); th = type * H + head; j = position inside the item
     auto decode = [&](int item, int j, int& b, int& h, int& rb, int& kb) {
-        if (MODE == 0) {   // item = (b, h, rb), j = kb
-            rb = item % nblk; const int r = item / nblk; h = r % p.H; b = r / p.H; kb = j;
-        } else {           // item = (b, rb, kb), j = h
+        if (MODE == 0) {   // item = (b, th, rb), j = kb
+            rb = item % nblk; const int r = item / nblk; h = r % TH; b = r / TH; kb = j;
+        } else {           // item = (b, rb, kb), j = th
             kb = item % nblk; const int r = item / nblk; rb = r % nblk; b = r / nblk; h = j;
         }
     };
@@ -87,10 +88,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     uint8_t* st = tiles + s * kAStage;
                     mbar_arrive_expect_tx(&full_bar[s], kAStage);
                     const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
-                    tma_load_2d(st, &tmQ, &full_bar[s], p.xo + h * kABK, xr);
-                    tma_load_2d(st + kATile, &tmQ, &full_bar[s], p.xo + p.lo_off + h * kABK, xr);
-                    tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], p.yo + h * kABK, yr);
-                    tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], p.yo + p.lo_off + h * kABK, yr);
+                    const int ty = h / p.H, hd = h - ty * p.H;
+                    const int xc = p.xo[ty] + hd * kABK, yc = p.yo[ty] + hd * kABK;
+                    tma_load_2d(st, &tmQ, &full_bar[s], xc, xr);
+                    tma_load_2d(st + kATile, &tmQ, &full_bar[s], xc + p.lo_off, xr);
+                    tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], yc, yr);
+                    tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], yc + p.lo_off, yr);
                 }
         }
     } else if (warp == 1) {
@@ -143,7 +146,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const int buf = it & 1;
                 float m_row = 0.f, linv = 0.f;
                 if (MODE == 1 && row_ok) {
-                    const int64_t si = ((int64_t)b * p.H + h) * p.N + row;
+                    const int ty = h / p.H, hd = h - ty * p.H;
+                    const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
                     m_row = __ldg(p.m + si);
                     linv = 1.f / __ldg(p.l + si);
                 }
@@ -220,21 +224,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const float m1 = xch[trow], l1 = xch[128 + trow];
                     const float mf = fmaxf(m_run, m1);
                     const float lf = l_run * exp2f(m_run - mf) + l1 * exp2f(m1 - mf);
-                    const int64_t si = ((int64_t)b * p.H + h) * p.N + row;
+                    const int ty = h / p.H, hd = h - ty * p.H;
+                    const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
                     p.m[si] = mf;
                     p.l[si] = lf;
                 }
                 bar_sync(3, 256);
-            } else if (row_ok) {
-                // head-reduced map: out[b,row,key] (+)= coef * sum_h p ; each thread writes its own row segment
-                float* o = p.out + ((int64_t)b * p.N + row) * p.N;
+            } else {
+                // head-reduced map out[b,row,key] = coef * sum p: staged per 32-column chunk in the team's buffer
+                // (pitch 33 floats) and written with 8 lanes per row segment -> 128 B coalesced stores
+                float* stg = reinterpret_cast<float*>(tbuf);
+                const int tid = (ew & 3) * 32 + lane, sub = tid >> 3, c4 = (tid & 7) * 4;
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
                     const int key0 = kb * 128 + (half * 2 + cc) * 32;
+                    if (key0 >= p.N) continue;  // (uniform)
+                    if (leader) tma_store_wait_read<0>();  // P stores may still be reading the staging buffers
+                    bar_sync(team_bar, 128);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e)
-                        if (key0 + e < p.N) o[key0 + e] = p.accumulate ? o[key0 + e] + p.coef * acc[cc][e] : p.coef * acc[cc][e];
+                    for (int e = 0; e < 32; ++e) stg[trow * 33 + e] = p.coef * acc[cc][e];
+                    bar_sync(team_bar, 128);
+                    for (int rr = sub; rr < 128; rr += 16) {
+                        const int orow = rb * 128 + rr;
+                        if (orow >= p.N) break;
+                        float* o = p.out + ((int64_t)b * p.N + orow) * p.N + key0 + c4;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (key0 + c4 + e < p.N) o[e] = stg[rr * 33 + c4 + e];
+                    }
                 }
+                bar_sync(team_bar, 128);  // staging buffers are reused by the next item's P tiles
             }
         }
         if (MODE == 1 && leader) tma_store_wait_read<0>();
@@ -254,7 +273,8 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
         XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
         attr_set = true;
     }
-    XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N, "attn_scores: bad shape");
+    XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.ntypes >= 1 && p.ntypes <= 3 &&
+                   (!p.write_p || p.ntypes == 1), "attn_scores: bad shape");
     XL_REQUIRE(p.m && p.l && p.out, "attn_scores: missing buffers");
     const int nblk = (p.N + 127) / 128;
     CUtensorMap tmP = tmQ;
@@ -266,7 +286,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
         if (int e = encode_tensor_map(&tmP, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, Ps, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
             return e;
     }
-    const int items0 = p.B * p.H * nblk, items1 = p.B * nblk * nblk;
+    const int items0 = p.B * p.ntypes * p.H * nblk, items1 = p.B * nblk * nblk;
     attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);
     if (int e = check_launch("attn_tc_kernel<stats>")) return e;
     attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);

@@ -11,13 +11,14 @@ namespace xl {
 // qkv matrix [B*N, 2*lo_off] (hi | lo).  alpha = scale * log2(e) (the kernels work in the exp2 domain).
 struct AttnParams {
     int B, H, N, np;        // np = round_up(N, 64): key pitch of the P operand
-    int xo, yo, lo_off;
+    int ntypes;             // score sets summed into `out` by one launch (1, or 3 for the surgery new path: qq, kk, vv)
+    int xo[3], yo[3];       // column offsets of X / Y per score set
+    int lo_off;
     float alpha;
-    float *m, *l;           // [B,H,N] row max (log2 domain) / row sum: written by the stats pass, read by the probs pass
-    float* out;             // [B,N,N]: (+)= coef * sum_h P[b,h]
+    float *m, *l;           // [ntypes,B,H,N] row max (log2 domain) / row sum: written by the stats pass, read by the probs pass
+    float* out;             // [B,N,N] = coef * sum_types sum_h P[b,h]
     float coef;
-    int accumulate;
-    int write_p;            // also emit the split-fp16 P operand [B*H*N, 2*np] (scaled by 2^10) for the P V GEMM
+    int write_p;            // also emit the split-fp16 P operand [B*H*N, 2*np] (scaled by 2^10) for the P V GEMM (ntypes == 1)
 };
 
 int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st);

@@ -156,7 +156,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
     size_t t = 0;
     t += align256((size_t)N * D * 4);                 // pos
-    t += 2 * align256((size_t)B * H * N * 4);         // softmax row stats m, l
+    t += 2 * align256((size_t)3 * B * H * N * 4);     // softmax row stats m, l (up to 3 score sets)
     t += align256((size_t)B * N * N * 4);             // pnew
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
@@ -196,13 +196,14 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     return tc_gemm(ma, mw, p, 1, 128, c.st);
 }
 
-// P[b,h] = softmax(scale * X_h Y_h^T) for X, Y column blocks (offsets xo, yo) of qkv_s, never materialising the
-// scores (attn_tc.cu): the head-reduced map out[b] (+)= coef * sum_h P[b,h], and (write_p) the split P operand
-static int scores(const Ctx& c, int xo, int yo, float scale, float* out, float coef, int accumulate, int write_p) {
+// out[b] = coef * sum over the score sets t and heads h of softmax(scale * X_t,h Y_t,h^T), X/Y column blocks (offsets
+// xo[t], yo[t]) of qkv_s, never materialising the scores (attn_tc.cu); write_p also emits the split P operand (1 set).
+static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float scale, float* out, float coef, int write_p) {
     AttnParams p = {};
-    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.xo = xo; p.yo = yo; p.lo_off = 3 * c.D;
+    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.ntypes = ntypes; p.lo_off = 3 * c.D;
+    for (int t = 0; t < ntypes; ++t) { p.xo[t] = xo[t]; p.yo[t] = yo[t]; }
     p.alpha = scale * 1.4426950408889634f;  // exp2 domain
-    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.accumulate = accumulate; p.write_p = write_p;
+    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.write_p = write_p;
     return attn_scores(c.m.qkv_a, p, write_p ? c.w.P : nullptr, c.st);
 }
 
@@ -275,8 +276,8 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         uint8_t* p = reinterpret_cast<uint8_t*>(workspace);
         auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
         c.w.pos = (float*)take((size_t)N * D * 4);
-        c.w.m = (float*)take((size_t)B * H * N * 4);
-        c.w.l = (float*)take((size_t)B * H * N * 4);
+        c.w.m = (float*)take((size_t)3 * B * H * N * 4);
+        c.w.l = (float*)take((size_t)3 * B * H * N * 4);
         c.w.pnew = (float*)take((size_t)B * N * N * 4);
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
@@ -329,6 +330,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         if (int e = check_launch("layernorm_kernel<embed>")) return e;
     }
 
+    const int qk_x[1] = {0}, qk_y[1] = {D}, self_xy[3] = {0, D, 2 * D};  // column blocks of qkv: q, k, v
     const float* x = c.w.x0;  // current single-path state (blocks before the surgery)
     for (int l = 0; l < L; ++l) {
         const ExcelVitLayer& Lw = Wt->blocks[l];
@@ -346,7 +348,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
             if (int e = qkv_stage(c, x, Lw, m_in)) return e;
-            if (int e = scores(c, 0, D, scale, attn_l, 1.f / H, 0, 1)) return e;  // need_weights: head mean
+            if (int e = scores(c, 1, qk_x, qk_y, scale, attn_l, 1.f / H, 1)) return e;  // need_weights: head mean
             if (int e = attn_v(c)) return e;
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
@@ -356,8 +358,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
             if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
-            for (int t = 0; t < 3; ++t)
-                if (int e = scores(c, t * D, t * D, scale, c.w.pnew, 1.f / 3.f, t > 0, 0)) return e;
+            if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, 0)) return e;
             if (int e = split_f16(c.w.pnew, N, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
@@ -367,7 +368,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                 if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
-            if (int e = scores(c, 0, D, scale, attn_l, 1.f, 0, 1)) return e;
+            if (int e = scores(c, 1, qk_x, qk_y, scale, attn_l, 1.f, 1)) return e;
             if (int e = attn_v(c)) return e;                                  // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
