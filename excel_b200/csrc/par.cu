@@ -60,14 +60,14 @@ __host__ __device__ constexpr int tap_dx(int t) { return (t == 0 || t == 3 || t 
 // cp_async_wait_all() + a barrier.
 __device__ __forceinline__ void stage_tile_async(float* sm, const float* __restrict__ src, int64_t plane_stride, int64_t sy,
                                                  int nplanes, int x0, int y0, int halo, int TW, int TH, int H, int W,
-                                                 int tid) {
+                                                 int tid, int nwarps = 8) {
     const int lane = tid & 31, warp = tid >> 5;
     const int xl = x0 - halo;
     const bool inside = xl >= 0 && xl + TW <= W;
     for (int p = 0; p < nplanes; ++p) {
         const float* sp = src + p * plane_stride;
         float* dp = sm + p * TH * TW;
-        for (int r = warp; r < TH; r += 8) {
+        for (int r = warp; r < TH; r += nwarps) {
             const float* row = sp + (int64_t)clampi(y0 - halo + r, 0, H - 1) * sy;
             if (inside && ((reinterpret_cast<uintptr_t>(row + xl) & 15) == 0)) {
                 for (int c = lane * 4; c < TW; c += 128) cp_async16(dp + r * TW + c, row + xl + c);
@@ -168,7 +168,6 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
 //    with more planes loop (the affinity re-read then comes from L2).
 constexpr int kG = 2;        // taps per TMA stage (8 KB)
 constexpr int kStages = 4;   // ring depth: kStages-1 stages (24 KB per CTA, 48 KB per SM) in flight
-constexpr int kParThreads = 256 + 32;  // 8 consumer warps + 1 TMA producer warp
 
 // shared-memory loads on 32-bit shared addresses (keeps the address arithmetic 32-bit; `volatile` pins
 // them behind the mbarrier waits)
@@ -217,12 +216,12 @@ __device__ __forceinline__ void load4_shift(uint32_t p, float (&m)[4]) {
 // 0 = dilation % 4 == 0 (aligned LDS.128); -1 = any dilation (scalar loads).
 // as: byte address of this thread's affinities in the stage; ctr[c]: byte address of its centre pixel in
 // plane c; d4 / dW4: byte offsets of one dilation step in x / y.
-template <int CCH, int MODE, int T0>
+template <int CCH, int TY, int MODE, int T0>
 __device__ __forceinline__ void par_taps(uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float (&acc)[4][CCH]) {
 #pragma unroll
     for (int tt = 0; tt < kG; ++tt) {
         const int t = T0 + tt;
-        const float4 a4 = lds128(as + tt * kTY * kTX * 4);
+        const float4 a4 = lds128(as + tt * TY * kTX * 4);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const int dy = tap_dy(t), dx = tap_dx(t);
 #pragma unroll
@@ -245,23 +244,24 @@ __device__ __forceinline__ void par_taps(uint32_t as, const uint32_t (&ctr)[CCH]
     }
 }
 
-template <int CCH, int T0>
+template <int CCH, int TY, int T0>
 __device__ __forceinline__ void par_taps_mode(int mode, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4,
                                               float (&acc)[4][CCH]) {
-    if (mode == 0) par_taps<CCH, 0, T0>(as, ctr, d4, dW4, acc);
-    else if (mode == 1) par_taps<CCH, 1, T0>(as, ctr, d4, dW4, acc);
-    else if (mode == 2) par_taps<CCH, 2, T0>(as, ctr, d4, dW4, acc);
-    else par_taps<CCH, -1, T0>(as, ctr, d4, dW4, acc);
+    if (mode == 0) par_taps<CCH, TY, 0, T0>(as, ctr, d4, dW4, acc);
+    else if (mode == 1) par_taps<CCH, TY, 1, T0>(as, ctr, d4, dW4, acc);
+    else if (mode == 2) par_taps<CCH, TY, 2, T0>(as, ctr, d4, dW4, acc);
+    else par_taps<CCH, TY, -1, T0>(as, ctr, d4, dW4, acc);
 }
 
 // Replicate padding for a tile that TMA zero-filled outside the image: copy the nearest in-image
 // column, then the nearest in-image row, inside shared memory.  Called by the 256 consumer threads.
-__device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, int TW, int TH, int H, int W, int tid) {
+__device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, int TW, int TH, int H, int W, int tid,
+                                           int nwarps) {
     const int lane = tid & 31, warp = tid >> 5;
     const int c_lo = max(0, -xl), c_hi = min(TW, W - xl) - 1;
     const int r_lo = max(0, -yl), r_hi = min(TH, H - yl) - 1;
     if (c_lo > 0 || c_hi < TW - 1) {
-        for (int q = warp; q < np * TH; q += 8) {
+        for (int q = warp; q < np * TH; q += nwarps) {
             const int r = q % TH;
             if (r < r_lo || r > r_hi) continue;
             float* row = sm + q * TW;
@@ -270,9 +270,9 @@ __device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, in
             for (int c = c_hi + 1 + lane; c < TW; c += 32) row[c] = vr;
         }
     }
-    bar_sync(1, 256);
+    bar_sync(1, nwarps * 32);
     if (r_lo > 0 || r_hi < TH - 1) {
-        for (int q = warp; q < np * TH; q += 8) {
+        for (int q = warp; q < np * TH; q += nwarps) {
             const int r = q % TH;
             if (r >= r_lo && r <= r_hi) continue;
             const float* srow = sm + (q - r + (r < r_lo ? r_lo : r_hi)) * TW;
@@ -280,54 +280,58 @@ __device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, in
             for (int c = lane; c < TW; c += 32) row[c] = srow[c];
         }
     }
-    bar_sync(1, 256);
+    bar_sync(1, nwarps * 32);
 }
 
-template <int CCH>
-__global__ void __launch_bounds__(kParThreads, 2)
+// TY = tile height (32 rows, or 16 for CCH = 4 so that two CTAs still fit one SM); NST = ring depth.
+template <int CCH, int TY, int NST>
+__global__ void __launch_bounds__(8 * TY + 32, 2)
 par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_constant__ CUtensorMap tm_in, int tma_in,
                    const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ plane_off, int img0,
                    int H, int W, int halo, ParGeom g) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tile_full, tile_empty;
-    // [kStages][kG][kTY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
+    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], tile_full, tile_empty;
+    constexpr int NC = 8 * TY, NW = TY / 4;  // consumer threads / warps
+    // [NST][kG][TY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
     // (offset arithmetic, not an integer round trip, so the compiler keeps the shared address space)
     float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    float* sm = ring + kStages * kG * kTY * kTX;
-    const int TW = kTX + 2 * halo, TH = kTY + 2 * halo, cs = TH * TW;
-    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = img0 + blockIdx.z;
+    float* sm = ring + NST * kG * TY * kTX;
+    const int TW = kTX + 2 * halo, TH = TY + 2 * halo, cs = TH * TW;
+    const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * TY, b = img0 + blockIdx.z;
     const int tid = threadIdx.x;
     const int K = 8 * g.n_dil, nchunk = K / kG;
     const int64_t plane = (int64_t)H * W;
     const int pbeg = plane_off[b], pend = plane_off[b + 1];
     const int npass = (pend - pbeg + CCH - 1) / CCH;
-    constexpr uint32_t kStageBytes = kG * kTY * kTX * sizeof(float);
+    constexpr uint32_t kStageBytes = kG * TY * kTX * sizeof(float);
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 8);
+            mbar_init(&empty_bar[s], NW);
         }
         mbar_init(&tile_full, 1);
-        mbar_init(&tile_empty, 8);
+        mbar_init(&tile_empty, NW);
         fence_barrier_init();
     }
     __syncthreads();
 
-    if (tid >= 256) {  // ---- producer warp: one lane drives TMA
-        if (tid == 256) {
+    if (tid >= NC) {  // ---- producer warp: one lane drives TMA
+        if (tid == NC) {
             int i = 0;
             for (int pass = 0; pass < npass; ++pass) {
                 if (tma_in) {  // mask tile (+halo) of this pass; zero-filled outside the image
                     if (pass > 0) mbar_wait(&tile_empty, (pass - 1) & 1);
                     mbar_arrive_expect_tx(&tile_full, (uint32_t)(CCH * cs * sizeof(float)));
-                    tma_load_3d(sm, &tm_in, &tile_full, x0 - halo, y0 - halo, pbeg + pass * CCH);
+                    tma_load_3d_hint(sm, &tm_in, &tile_full, x0 - halo, y0 - halo, pbeg + pass * CCH, kEvictLast);
                 }
                 for (int ch = 0; ch < nchunk; ++ch, ++i) {  // affinity chunks through the ring
-                    const int s = i % kStages;
-                    if (i >= kStages) mbar_wait(&empty_bar[s], ((i / kStages) - 1) & 1);
+                    const int s = i % NST;
+                    if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
-                    tma_load_3d(ring + s * kG * kTY * kTX, &tm_aff, &full_bar[s], x0, y0, (int)blockIdx.z * K + ch * kG);
+                    // the affinity planes are a pure stream: evict-first keeps the (re-read) mask planes in L2
+                    tma_load_3d_hint(ring + s * kG * TY * kTX, &tm_aff, &full_bar[s], x0, y0, (int)blockIdx.z * K + ch * kG,
+                                     kEvictFirst);
                 }
             }
         }
@@ -336,7 +340,7 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
 
     // ---- consumers: thread (tx4, ty) owns pixels (y0+ty, x0+4*tx4 .. +3)
     const int tx4 = tid & 7, ty = tid >> 3;
-    const bool border = x0 - halo < 0 || y0 - halo < 0 || x0 + kTX + halo > W || y0 + kTY + halo > H;
+    const bool border = x0 - halo < 0 || y0 - halo < 0 || x0 + kTX + halo > W || y0 + TY + halo > H;
     uint32_t ctr[CCH];
 #pragma unroll
     for (int c = 0; c < CCH; ++c) ctr[c] = smem_u32(sm + c * cs + (ty + halo) * TW + 4 * tx4 + halo);
@@ -347,12 +351,12 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
         const int np = min(CCH, pend - pc);
         if (tma_in) {
             mbar_wait(&tile_full, pass & 1);
-            if (border) fix_border(sm, CCH, x0 - halo, y0 - halo, TW, TH, H, W, tid);
+            if (border) fix_border(sm, CCH, x0 - halo, y0 - halo, TW, TH, H, W, tid, NW);
         } else {
-            if (pass > 0) bar_sync(1, 256);
-            stage_tile_async(sm, in + (int64_t)pc * plane, plane, W, np, x0, y0, halo, TW, TH, H, W, tid);
+            if (pass > 0) bar_sync(1, NC);
+            stage_tile_async(sm, in + (int64_t)pc * plane, plane, W, np, x0, y0, halo, TW, TH, H, W, tid, NW);
             cp_async_wait_all();
-            bar_sync(1, 256);
+            bar_sync(1, NC);
         }
         float acc[4][CCH];
 #pragma unroll
@@ -366,13 +370,13 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
             const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
 #pragma unroll
             for (int q = 0; q < 8 / kG; ++q) {
-                const int s = it % kStages;
-                mbar_wait(&full_bar[s], (it / kStages) & 1);
+                const int s = it % NST;
+                mbar_wait(&full_bar[s], (it / NST) & 1);
                 const uint32_t as = as0 + s * kStageBytes;
-                if (q == 0) par_taps_mode<CCH, 0 * kG>(mode, as, ctr, d4, dW4, acc);
-                else if (q == 1) par_taps_mode<CCH, 1 * kG>(mode, as, ctr, d4, dW4, acc);
-                else if (q == 2) par_taps_mode<CCH, 2 * kG>(mode, as, ctr, d4, dW4, acc);
-                else par_taps_mode<CCH, 3 * kG>(mode, as, ctr, d4, dW4, acc);
+                if (q == 0) par_taps_mode<CCH, TY, 0 * kG>(mode, as, ctr, d4, dW4, acc);
+                else if (q == 1) par_taps_mode<CCH, TY, 1 * kG>(mode, as, ctr, d4, dW4, acc);
+                else if (q == 2) par_taps_mode<CCH, TY, 2 * kG>(mode, as, ctr, d4, dW4, acc);
+                else par_taps_mode<CCH, TY, 3 * kG>(mode, as, ctr, d4, dW4, acc);
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with stage s
                 ++it;
@@ -477,15 +481,20 @@ static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy,
     return check_launch("par_affinity_kernel");
 }
 
+// tile height / ring depth per channel count: CCH = 4 uses half-height tiles so that two CTAs still share an SM
+__host__ __device__ constexpr int par_ty(int cch) { return cch >= 4 ? 16 : 32; }
+__host__ __device__ constexpr int par_nst(int cch) { return cch >= 4 ? 6 : 4; }
+
 template <int CCH>
 static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, const float* in, float* out,
                             const int* plane_off, int img0, int nimg, int H, int W, const ParGeom& g, cudaStream_t st) {
+    constexpr int TY = par_ty(CCH), NST = par_nst(CCH);
     const int halo = max_dilation(g);
-    const size_t smem = tile_smem_bytes(halo, CCH) + kStages * kG * kTY * kTX * sizeof(float) + 128;
-    if (int e = set_smem(par_iterate_kernel<CCH>, smem, "par_iterate")) return e;
-    dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), nimg);
-    par_iterate_kernel<CCH><<<grid, kParThreads, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out, plane_off,
-                                                             img0, H, W, halo, g);
+    const size_t smem = (size_t)(kTX + 2 * halo) * (TY + 2 * halo) * CCH * sizeof(float) + NST * kG * TY * kTX * sizeof(float) + 128;
+    if (int e = set_smem(par_iterate_kernel<CCH, TY, NST>, smem, "par_iterate")) return e;
+    dim3 grid(ceil_div(W, kTX), ceil_div(H, TY), nimg);
+    par_iterate_kernel<CCH, TY, NST><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
+                                                                      plane_off, img0, H, W, halo, g);
     return check_launch("par_iterate_kernel");
 }
 
@@ -495,7 +504,8 @@ static int launch_iterate(const CUtensorMap& tm, const CUtensorMap* tm_in, const
     switch (cch) {
         case 1: return launch_iterate_c<1>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
         case 2: return launch_iterate_c<2>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
-        default: return launch_iterate_c<3>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
+        case 3: return launch_iterate_c<3>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
+        default: return launch_iterate_c<4>(tm, tm_in, in, out, plane_off, img0, nimg, H, W, g, st);
     }
 }
 
@@ -543,13 +553,13 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         img = resize_ws;
         stride_y = W; stride_c = (int64_t)H * W; stride_b = 3 * stride_c;
     }
-    const int cch = max_c < 3 ? max_c : 3;
+    const int cch = max_c < 4 ? max_c : 4;
     const int Wp = (W + 3) & ~3;  // row pitch of the affinity workspace
     CUtensorMap tm;
     if (iterate) {
         const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)group * 8 * n_dil};
         const uint64_t strides[2] = {(uint64_t)Wp * 4, (uint64_t)Wp * H * 4};
-        const uint32_t box[3] = {kTX, kTY, kG};
+        const uint32_t box[3] = {kTX, (uint32_t)par_ty(cch), kG};
         if (int e = encode_tensor_map(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, aff_ws, dims, strides, box,
                                       CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     }
@@ -564,7 +574,7 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         const int halo = max_dilation(g);
         const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)total_planes};
         const uint64_t strides[2] = {(uint64_t)W * 4, (uint64_t)W * H * 4};
-        const uint32_t box[3] = {(uint32_t)(kTX + 2 * halo), (uint32_t)(kTY + 2 * halo), (uint32_t)cch};
+        const uint32_t box[3] = {(uint32_t)(kTX + 2 * halo), (uint32_t)(par_ty(cch) + 2 * halo), (uint32_t)cch};
         for (int i = 0; i < 3; ++i)
             if (bufs[i])
                 if (int e = encode_tensor_map(&tm_planes[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bufs[i], dims, strides, box,
