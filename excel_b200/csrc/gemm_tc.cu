@@ -31,7 +31,7 @@ namespace xl {
 constexpr int kBK = 64, kTcStages = 3;
 constexpr uint32_t kTileBytes = kBM * kBK * 2;        // one 128-row x 64-k fp16 tile: 16 KB
 constexpr uint32_t kStageBytes = 4 * kTileBytes;      // A_hi, A_lo, B_hi, B_lo (B tiles use BN*128 B of their slot)
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 64 + 256;                 // TMA producer warp, MMA warp, 8 epilogue warps
 constexpr uint32_t kEpiBytes = 2 * 16384;             // epilogue staging: two 128-row x 128 B blocks (TMA store sources)
 constexpr size_t kTcSmem = kTcStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -66,7 +66,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 4);  // one arrival per epilogue warp
+            mbar_init(&acc_empty[s], TMA_EPI ? 8 : 4);  // one arrival per (active) epilogue warp
         }
         fence_barrier_init();
     }
@@ -132,8 +132,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ---- epilogue (warps 2..5).  Warp w owns TMEM lanes 32*(w%4)..+31 == tile rows 32*(w%4)+lane.
-        const int lg = warp & 3;
+        // ---- epilogue (warps 2..9).  Warp w owns TMEM lanes 32*(w%4)..+31 == tile rows 32*(w%4)+lane; the two teams
+        // of four warps (2..5, 6..9) take alternate 32-column chunks of the tile.
+        const int lg = warp & 3, team = (warp - 2) >> 2;
         const int trow = lg * 32 + lane;
         const float alpha = p.alpha;
         const int act = p.act;
@@ -141,11 +142,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int i = 0;
         if constexpr (TMA_EPI) {
             // Per 32-column chunk each thread pulls its row slice out of TMEM, applies alpha / bias / QuickGELU /
-            // residual and writes it into a swizzled staging buffer (two, alternating); one elected thread then
-            // hands the 128 x 32 block to the TMA store engine, which also clips rows >= M and columns >= N.
-            uint8_t* ebuf = reinterpret_cast<uint8_t*>(stage);
-            const bool leader = threadIdx.x == 64;
-            int ck = 0;  // running chunk counter -> staging buffer parity
+            // residual and writes it into its team's swizzled staging buffer; the team's elected thread then hands
+            // the 128 x 32 block to the TMA store engine, which also clips rows >= M and columns >= N.
+            uint8_t* sb = reinterpret_cast<uint8_t*>(stage) + team * 16384;
+            const bool leader = lane == 0 && ((warp - 2) & 3) == 0;
+            const int team_bar = 1 + team;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
                 int m0, n0, z1, z2;
                 decode(t, m0, n0, z1, z2);
@@ -155,25 +156,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float* resrow = p.residual ? p.residual + (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2 + (int64_t)(m0 + trow) * p.ldc : nullptr;
                 const bool row_ok = m0 + trow < p.M;
 #pragma unroll 1
-                for (int c = 0; c < kBN / 32; ++c, ++ck) {
+                for (int c = team; c < kBN / 32; c += 2) {
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * kBN + c * 32), r);
-                    if (c == kBN / 32 - 1) {  // all of this thread's TMEM reads for the tile are done
+                    if (c + 2 >= kBN / 32) {  // all of this warp's TMEM reads for the tile are done
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
                     }
                     const int nb = n0 + c * 32;
-                    if (nb >= p.N) continue;   // (uniform) nothing to store for this chunk
-                    uint8_t* sb = ebuf + (ck & 1) * 16384;
-                    if (leader) tma_store_wait_read<1>();  // the store that last read this buffer has drained
-                    bar_sync(1, 128);
+                    if (nb >= p.N) continue;   // (team-uniform) nothing to store for this chunk
+                    if (leader) tma_store_wait_read<0>();  // the store that last read the team's buffer has drained
+                    bar_sync(team_bar, 128);
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float x = alpha * __uint_as_float(r[j]);
                         if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
-                        if (act == 1) x = x * (1.f / (1.f + expf(-1.702f * x)));  // QuickGELU
+                        // QuickGELU x * sigmoid(1.702 x) (clip_surgery_model.py:280-282), exp2 domain
+                        if (act == 1) x = x * __frcp_rn(1.f + exp2f(-2.4554669595930156f * x));
                         v[j] = x;
                     }
                     if (p.C) {
@@ -213,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     fence_proxy_async_smem();
-                    bar_sync(1, 128);
+                    bar_sync(team_bar, 128);
                     if (leader) {
                         if (p.C) {
                             tma_store_4d(&tmC, sb, nb, m0, z2, z1);
@@ -227,9 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
             if (leader) tma_store_wait_read<0>();
-        } else {
-        // Fallback for outputs TMA cannot address (row pitch not a multiple of 16 B): stage 128 x 32 blocks in shared
-        // memory (pitch 36 floats) and stream them out with 8 lanes per row (128 B segments).
+        } else if (team == 0) {
+        // Fallback for outputs TMA cannot address (row pitch not a multiple of 16 B), warps 2..5 only: stage 128 x 32
+        // blocks in shared memory (pitch 36 floats) and stream them out with 8 lanes per row (128 B segments).
         constexpr int kPitch = 36;
         const int ew = warp - 2, sub = lane >> 3, c4 = (lane & 7) * 4;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
@@ -257,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 4; ++e) {
                         float x = alpha * __uint_as_float(r[j + e]);
                         if (bias && nb + j + e < p.N) x += __ldg(bias + nb + j + e);
-                        if (act == 1) x = x * (1.f / (1.f + expf(-1.702f * x)));  // QuickGELU
+                        if (act == 1) x = x * __frcp_rn(1.f + exp2f(-2.4554669595930156f * x));  // QuickGELU
                         v[e] = x;
                     }
                     *reinterpret_cast<float4*>(stage + trow * kPitch + j) = make_float4(v[0], v[1], v[2], v[3]);
