@@ -27,7 +27,13 @@ constexpr uint32_t kAStage = 4 * kATile;                  // X_hi, X_lo, Y_hi, Y
 constexpr uint32_t kAEpi = 4 * 16384;                     // 2 teams x 2 TMA-store staging buffers
 constexpr int kAThreads = 64 + 256;
 constexpr size_t kASmem = kAStages * kAStage + kAEpi + 2048 /*row stats exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
-constexpr float kProbScaleA = 1024.f;                     // must match vit.cu: kProbScale
+constexpr float kProbScaleA = 1024.f;                     // 2^10; must match vit.cu: kProbScale
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kAThreads, 1)
@@ -144,12 +150,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             for (int j = 0; j < inner; ++j, ++it) {
                 decode(item, j, b, h, rb, kb);
                 const int buf = it & 1;
-                float m_row = 0.f, linv = 0.f;
+                float m_row = INFINITY;   // rows past N: exp2(-inf) = 0
                 if (MODE == 1 && row_ok) {
                     const int ty = h / p.H, hd = h - ty * p.H;
                     const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
-                    m_row = __ldg(p.m + si);
-                    linv = 1.f / __ldg(p.l + si);
+                    m_row = __ldg(p.m + si) + __log2f(__ldg(p.l + si)) - 10.f;   // folds 1/l and the 2^10 operand scale
                 }
                 mbar_wait(&acc_full[buf], (it >> 1) & 1);
                 tc_fence_after();
@@ -164,28 +169,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
                     }
                     const int key0 = kb * 128 + c * 32;
+                    const bool full = key0 + 32 <= p.N;   // (uniform) no key of this chunk is padding
                     if (MODE == 0) {
-                        float s[32], cmax = -INFINITY;
+                        // running row max / sum in the exp2 domain; alpha > 0, so max(alpha*a) = alpha*max(a)
+                        float cmax = -INFINITY;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            s[e] = key0 + e < p.N ? p.alpha * __uint_as_float(r[e]) : -INFINITY;
-                            cmax = fmaxf(cmax, s[e]);
-                        }
-                        const float m_new = fmaxf(m_run, cmax);
+                        for (int e = 0; e < 32; ++e)
+                            if (full || key0 + e < p.N) cmax = fmaxf(cmax, __uint_as_float(r[e]));
+                        const float m_new = fmaxf(m_run, p.alpha * cmax);
                         if (m_new > -INFINITY) {
                             float sum = 0.f;
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) sum += exp2f(s[e] - m_new);
-                            l_run = l_run * exp2f(m_run - m_new) + sum;
+                            for (int e = 0; e < 32; ++e) {
+                                const float ex = ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_new));
+                                sum += (full || key0 + e < p.N) ? ex : 0.f;
+                            }
+                            l_run = l_run * ex2_approx(m_run - m_new) + sum;
                             m_run = m_new;
                         }
                     } else {
+                        // pr = 2^10 * p = exp2(alpha*s - (m + log2 l - 10)): one FFMA + one MUFU per element
                         float pr[32];
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const float v = (row_ok && key0 + e < p.N) ? exp2f(p.alpha * __uint_as_float(r[e]) - m_row) * linv : 0.f;
-                            pr[e] = v;
-                            acc[cc][e] += v;
+                            const float v = ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_row));
+                            pr[e] = (full || key0 + e < p.N) ? v : 0.f;
+                            acc[cc][e] += pr[e];
                         }
                         if (p.write_p && key0 < p.np) {  // (uniform) P operand tile: split fp16, scaled, via TMA store
                             uint8_t* sb = tbuf + (ck & 1) * 16384;
@@ -193,12 +202,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             bar_sync(team_bar, 128);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                __align__(16) __half hh[8], ll[8];
+                                __align__(16) __half2 hh[4], ll[4];
 #pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    const float v = pr[8 * q + e] * kProbScaleA;
-                                    hh[e] = __float2half_rn(v);
-                                    ll[e] = __float2half_rn(v - __half2float(hh[e]));
+                                for (int e = 0; e < 4; ++e) {
+                                    const float v0 = pr[8 * q + 2 * e], v1 = pr[8 * q + 2 * e + 1];
+                                    hh[e] = __floats2half2_rn(v0, v1);
+                                    const float2 hf = __half22float2(hh[e]);
+                                    ll[e] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
                                 }
                                 const int off = trow * 64 + ((q ^ ((trow >> 1) & 3)) << 4);   // SWIZZLE_64B
                                 *reinterpret_cast<uint4*>(sb + off) = *reinterpret_cast<const uint4*>(hh);
@@ -223,7 +233,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (half == 0 && row_ok) {
                     const float m1 = xch[trow], l1 = xch[128 + trow];
                     const float mf = fmaxf(m_run, m1);
-                    const float lf = l_run * exp2f(m_run - mf) + l1 * exp2f(m1 - mf);
+                    const float lf = l_run * ex2_approx(m_run - mf) + l1 * ex2_approx(m1 - mf);
                     const int ty = h / p.H, hd = h - ty * p.H;
                     const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
                     p.m[si] = mf;
@@ -242,7 +252,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if (leader) tma_store_wait_read<0>();  // P stores may still be reading the staging buffers
                     bar_sync(team_bar, 128);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) stg[trow * 33 + e] = p.coef * acc[cc][e];
+                    for (int e = 0; e < 32; ++e) stg[trow * 33 + e] = (p.coef * (1.f / kProbScaleA)) * acc[cc][e];
                     bar_sync(team_bar, 128);
                     for (int rr = sub; rr < 128; rr += 16) {
                         const int orow = rb * 128 + rr;
