@@ -166,8 +166,7 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
 //    compile-time-shifted LDS.128/LDS.64/LDS.32 combination for dilations 1 and 2.
 //  * CCH mask planes (+ halo, replicate padding applied at load) are staged in shared memory; images
 //    with more planes loop (the affinity re-read then comes from L2).
-constexpr int kG = 2;        // taps per TMA stage (8 KB)
-constexpr int kStages = 4;   // ring depth: kStages-1 stages (24 KB per CTA, 48 KB per SM) in flight
+// Ring geometry (par_ty / par_nst / par_kg below): 4 KB TMA stages; NST-1 of them in flight per CTA.
 
 // shared-memory loads on 32-bit shared addresses (keeps the address arithmetic 32-bit; `volatile` pins
 // them behind the mbarrier waits)
@@ -216,11 +215,11 @@ __device__ __forceinline__ void load4_shift(uint32_t p, float (&m)[4]) {
 // 0 = dilation % 4 == 0 (aligned LDS.128); -1 = any dilation (scalar loads).
 // as: byte address of this thread's affinities in the stage; ctr[c]: byte address of its centre pixel in
 // plane c; d4 / dW4: byte offsets of one dilation step in x / y.
-template <int CCH, int TY, int MODE, int T0>
-__device__ __forceinline__ void par_taps(uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float (&acc)[4][CCH]) {
+template <int CCH, int TY, int KG, int MODE>
+__device__ __forceinline__ void par_taps(int t0, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float (&acc)[4][CCH]) {
 #pragma unroll
-    for (int tt = 0; tt < kG; ++tt) {
-        const int t = T0 + tt;
+    for (int tt = 0; tt < KG; ++tt) {
+        const int t = t0 + tt;  // compile-time after unrolling (the caller's q loop is unrolled too)
         const float4 a4 = lds128(as + tt * TY * kTX * 4);
         const float a[4] = {a4.x, a4.y, a4.z, a4.w};
         const int dy = tap_dy(t), dx = tap_dx(t);
@@ -244,13 +243,13 @@ __device__ __forceinline__ void par_taps(uint32_t as, const uint32_t (&ctr)[CCH]
     }
 }
 
-template <int CCH, int TY, int T0>
-__device__ __forceinline__ void par_taps_mode(int mode, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4,
+template <int CCH, int TY, int KG>
+__device__ __forceinline__ void par_taps_mode(int mode, int t0, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4,
                                               float (&acc)[4][CCH]) {
-    if (mode == 0) par_taps<CCH, TY, 0, T0>(as, ctr, d4, dW4, acc);
-    else if (mode == 1) par_taps<CCH, TY, 1, T0>(as, ctr, d4, dW4, acc);
-    else if (mode == 2) par_taps<CCH, TY, 2, T0>(as, ctr, d4, dW4, acc);
-    else par_taps<CCH, TY, -1, T0>(as, ctr, d4, dW4, acc);
+    if (mode == 0) par_taps<CCH, TY, KG, 0>(t0, as, ctr, d4, dW4, acc);
+    else if (mode == 1) par_taps<CCH, TY, KG, 1>(t0, as, ctr, d4, dW4, acc);
+    else if (mode == 2) par_taps<CCH, TY, KG, 2>(t0, as, ctr, d4, dW4, acc);
+    else par_taps<CCH, TY, KG, -1>(t0, as, ctr, d4, dW4, acc);
 }
 
 // Replicate padding for a tile that TMA zero-filled outside the image: copy the nearest in-image
@@ -284,7 +283,7 @@ __device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, in
 }
 
 // TY = tile height (32 rows, or 16 for CCH = 4 so that two CTAs still fit one SM); NST = ring depth.
-template <int CCH, int TY, int NST>
+template <int CCH, int TY, int NST, int KG>
 __global__ void __launch_bounds__(8 * TY + 32, 2)
 par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_constant__ CUtensorMap tm_in, int tma_in,
                    const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ plane_off, int img0,
@@ -292,18 +291,18 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], tile_full, tile_empty;
     constexpr int NC = 8 * TY, NW = TY / 4;  // consumer threads / warps
-    // [NST][kG][TY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
+    // [NST][KG][TY][kTX] affinity ring (128 B-aligned TMA destinations), then the mask tile
     // (offset arithmetic, not an integer round trip, so the compiler keeps the shared address space)
     float* ring = reinterpret_cast<float*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
-    float* sm = ring + NST * kG * TY * kTX;
+    float* sm = ring + NST * KG * TY * kTX;
     const int TW = kTX + 2 * halo, TH = TY + 2 * halo, cs = TH * TW;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * TY, b = img0 + blockIdx.z;
     const int tid = threadIdx.x;
-    const int K = 8 * g.n_dil, nchunk = K / kG;
+    const int K = 8 * g.n_dil, nchunk = K / KG;
     const int64_t plane = (int64_t)H * W;
     const int pbeg = plane_off[b], pend = plane_off[b + 1];
     const int npass = (pend - pbeg + CCH - 1) / CCH;
-    constexpr uint32_t kStageBytes = kG * TY * kTX * sizeof(float);
+    constexpr uint32_t kStageBytes = KG * TY * kTX * sizeof(float);
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -330,7 +329,7 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
                     if (i >= NST) mbar_wait(&empty_bar[s], ((i / NST) - 1) & 1);
                     mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
                     // the affinity planes are a pure stream: evict-first keeps the (re-read) mask planes in L2
-                    tma_load_3d_hint(ring + s * kG * TY * kTX, &tm_aff, &full_bar[s], x0, y0, (int)blockIdx.z * K + ch * kG,
+                    tma_load_3d_hint(ring + s * KG * TY * kTX, &tm_aff, &full_bar[s], x0, y0, (int)blockIdx.z * K + ch * KG,
                                      kEvictFirst);
                 }
             }
@@ -369,14 +368,11 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
             const int d4 = d * 4, dW4 = d * TW * 4;
             const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
 #pragma unroll
-            for (int q = 0; q < 8 / kG; ++q) {
+            for (int q = 0; q < 8 / KG; ++q) {
                 const int s = it % NST;
                 mbar_wait(&full_bar[s], (it / NST) & 1);
                 const uint32_t as = as0 + s * kStageBytes;
-                if (q == 0) par_taps_mode<CCH, TY, 0 * kG>(mode, as, ctr, d4, dW4, acc);
-                else if (q == 1) par_taps_mode<CCH, TY, 1 * kG>(mode, as, ctr, d4, dW4, acc);
-                else if (q == 2) par_taps_mode<CCH, TY, 2 * kG>(mode, as, ctr, d4, dW4, acc);
-                else par_taps_mode<CCH, TY, 3 * kG>(mode, as, ctr, d4, dW4, acc);
+                par_taps_mode<CCH, TY, KG>(mode, q * KG, as, ctr, d4, dW4, acc);
                 __syncwarp();
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with stage s
                 ++it;
@@ -483,17 +479,18 @@ static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy,
 
 // tile height / ring depth per channel count: CCH = 4 uses half-height tiles so that two CTAs still share an SM
 __host__ __device__ constexpr int par_ty(int cch) { return cch >= 4 ? 16 : 32; }
-__host__ __device__ constexpr int par_nst(int cch) { return cch >= 4 ? 6 : 4; }
+__host__ __device__ constexpr int par_nst(int cch) { return cch >= 4 ? 7 : 8; }   // ring depth
+__host__ __device__ constexpr int par_kg(int cch) { return cch >= 4 ? 2 : 1; }    // taps per stage (4 KB stages)
 
 template <int CCH>
 static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, const float* in, float* out,
                             const int* plane_off, int img0, int nimg, int H, int W, const ParGeom& g, cudaStream_t st) {
-    constexpr int TY = par_ty(CCH), NST = par_nst(CCH);
+    constexpr int TY = par_ty(CCH), NST = par_nst(CCH), KG = par_kg(CCH);
     const int halo = max_dilation(g);
-    const size_t smem = (size_t)(kTX + 2 * halo) * (TY + 2 * halo) * CCH * sizeof(float) + NST * kG * TY * kTX * sizeof(float) + 128;
-    if (int e = set_smem(par_iterate_kernel<CCH, TY, NST>, smem, "par_iterate")) return e;
+    const size_t smem = (size_t)(kTX + 2 * halo) * (TY + 2 * halo) * CCH * sizeof(float) + NST * KG * TY * kTX * sizeof(float) + 128;
+    if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG>, smem, "par_iterate")) return e;
     dim3 grid(ceil_div(W, kTX), ceil_div(H, TY), nimg);
-    par_iterate_kernel<CCH, TY, NST><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
+    par_iterate_kernel<CCH, TY, NST, KG><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
                                                                       plane_off, img0, H, W, halo, g);
     return check_launch("par_iterate_kernel");
 }
@@ -559,7 +556,7 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
     if (iterate) {
         const uint64_t dims[3] = {(uint64_t)W, (uint64_t)H, (uint64_t)group * 8 * n_dil};
         const uint64_t strides[2] = {(uint64_t)Wp * 4, (uint64_t)Wp * H * 4};
-        const uint32_t box[3] = {kTX, (uint32_t)par_ty(cch), kG};
+        const uint32_t box[3] = {kTX, (uint32_t)par_ty(cch), (uint32_t)par_kg(cch)};
         if (int e = encode_tensor_map(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, aff_ws, dims, strides, box,
                                       CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     }

@@ -27,11 +27,9 @@ def run(B, S, C, iters, group):
                           alg_GBs=round(bytes_alg / ms / 1e6, 1), img_per_s=round(B / ms * 1e3, 1))), flush=True)
 
 if __name__ == "__main__":
-    for group in (1, 2, 4, 0):
-        run(16, 512, 3, 20, group)
-    run(16, 512, 4, 20, 1)
-    run(16, 512, 2, 20, 1)
-    for group in (1, 0):
-        run(4, 1024, 4, 20, group)
+    for c in (2, 3, 4, 5):
+        run(16, 512, c, 20, 0)
+    run(16, 512, 3, 20, 1)
+    run(4, 1024, 4, 20, 0)
     run(4, 1024, 4, 1, 0); run(4, 1024, 4, 50, 0)
-    run(8, 448, 3, 20, 1)
+    run(8, 448, 3, 20, 0)
