@@ -23,9 +23,10 @@ def _class_lists(cls_labels):
     return [torch.where(row)[0].to(torch.int64) for row in host]
 
 
-def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers):
+def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None):
     """attr_maps [B,n_p,K]; attn [L,B,N,N] (arbitrary stride_l / stride_b, rows contiguous).
-    Returns refined [Q, n_p] for the Q = sum_b n_b (image, class) pairs, in image-major class-ascending order."""
+    Returns refined [Q, n_p] for the Q = sum_b n_b (image, class) pairs, image-major (images in `order`, default
+    0..B-1), classes ascending."""
     dev = attr_maps.device
     B, n_p, _ = attr_maps.shape
     L, _, N, _ = attn.shape
@@ -36,8 +37,9 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers):
     attr_maps = _f32(attr_maps)
     if attr_maps.stride(2) != 1:
         attr_maps = attr_maps.contiguous()
-    img_of = torch.tensor([b for b, c in enumerate(cls_lists) for _ in c], dtype=torch.int32)
-    cls_of = torch.cat(cls_lists).to(torch.int32) if cls_lists else torch.zeros(0, dtype=torch.int32)
+    order = list(range(len(cls_lists))) if order is None else order
+    img_of = torch.tensor([b for b in order for _ in cls_lists[b]], dtype=torch.int32)
+    cls_of = torch.cat([cls_lists[b] for b in order]).to(torch.int32) if cls_lists else torch.zeros(0, dtype=torch.int32)
     Q = int(img_of.numel())
     img_of, cls_of = img_of.to(dev, non_blocking=True), cls_of.to(dev, non_blocking=True)
     st = _lib.stream()
@@ -132,11 +134,25 @@ def refine_cams_with_bkg_weclip(cam_refined_list, inputs_denorm, cls_lst, par, s
     return labels, planes
 
 
+def _segments(counts):
+    """Runs of equal plane count (counts sorted ascending) -> [(b0, b1, planes_per_image)]; everything with more than
+    4 planes shares the last run (the PAR kernel stages at most 4 planes per pass)."""
+    segs, b0 = [], 0
+    for b in range(1, len(counts) + 1):
+        if b == len(counts) or min(counts[b], 5) != min(counts[b0], 5):
+            segs.append((b0, b, max(counts[b0:b])))
+            b0 = b
+    return segs
+
+
 def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=None, caa_thre=0.79, attn_layers=6,
                  return_cams=False):
     """Fused batched SVC + PAR + argmax (tools/infer_lam.py:88-94 for the whole batch).
     attr_maps [B,n_p,K], attn_weights [L,B,N,N], cls_labels [B,K], par_imgs [B,3,h,w].
-    Returns labels [B,H,W] int64 (and the packed planes, plane_off when return_cams)."""
+    Returns labels [B,H,W] int64 (and the packed planes, plane_off, refined CAMs when return_cams).
+
+    Images are processed in order of their plane count so that PAR launches run the kernel variant that fits
+    (2, 3 or 4 planes staged per pass); the labels come back in the caller's order."""
     B = attr_maps.shape[0]
     h, w = par_imgs.shape[-2:]
     H, W = (h, w) if out_size is None else (int(out_size[0]), int(out_size[1]))
@@ -145,13 +161,22 @@ def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=No
     counts = [int(c.numel()) for c in cls_lists]
     if min(counts) == 0:
         raise RuntimeError("stack expects a non-empty TensorList")  # an image without classes (affutils.py:63)
-    refined = _svc_vectors(attr_maps, attn_weights, cls_lists, gh, gw, caa_thre, attn_layers)
-    planes, plane_off, off = _cams_to_planes(refined, counts, gh, gw, H, W)
-    key = torch.cat([torch.cat([torch.zeros(1, dtype=torch.int64), c + 1]) for c in cls_lists]).to(planes.device,
-                                                                                                   non_blocking=True)
-    out = par_refine_planes(par_imgs, planes, plane_off, max(counts) + 1, par.dilations, par.num_iter,
-                            getattr(par, "group", 0), par.w1, par.w2)
+    order = list(range(B)) if return_cams else sorted(range(B), key=lambda b: counts[b])
+    identity = order == list(range(B))
+    counts_s = [counts[b] for b in order]
+    refined = _svc_vectors(attr_maps, attn_weights, cls_lists, gh, gw, caa_thre, attn_layers, order)
+    planes, plane_off, off = _cams_to_planes(refined, counts_s, gh, gw, H, W)
+    dev = planes.device
+    key = torch.cat([torch.cat([torch.zeros(1, dtype=torch.int64), cls_lists[b] + 1]) for b in order]).to(dev, non_blocking=True)
+    imgs_s = par_imgs if identity else par_imgs.index_select(0, torch.tensor(order, device=par_imgs.device))
+    segs = _segments([c + 1 for c in counts_s])
+    out = par_refine_planes(imgs_s, planes, plane_off, max(counts) + 1, par.dilations, par.num_iter,
+                            getattr(par, "group", 0), par.w1, par.w2, segments=segs)
     labels = par_labels(out, plane_off, key, B)
+    if not identity:
+        unsorted = torch.empty_like(labels)
+        unsorted.index_copy_(0, torch.tensor(order, device=dev), labels)
+        labels = unsorted
     if return_cams:
         return labels, planes, plane_off, refined
     return labels

@@ -16,9 +16,10 @@ def _pitch(w):
     return (w + 3) & ~3
 
 
-def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2):
+def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2, segments=None):
     """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
-    Returns the refined planes [P,H,W] (a new tensor)."""
+    segments: optional [(b0, b1, max planes per image)] runs of consecutive images launched separately (so that each
+    run gets the kernel variant matching its plane count).  Returns the refined planes [P,H,W] (a new tensor)."""
     imgs = imgs.float()
     if imgs.stride(-1) != 1:
         imgs = imgs.contiguous()
@@ -28,15 +29,19 @@ def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group
     if num_iter <= 0 or P == 0:
         return planes.clone()
     K = 8 * len(dilations)
-    g = B if group <= 0 else min(group, B)
+    segments = [(0, B, int(max_c))] if not segments else segments
+    nmax = max(b1 - b0 for b0, b1, _ in segments)
+    g = nmax if group <= 0 else min(group, nmax)
     dev = planes.device
     aff = torch.empty((g, K, H, _pitch(W)), dtype=torch.float32, device=dev)   # internal layout: row pitch % 4 == 0
-    rs = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
+    rs = torch.empty((nmax, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
     out = torch.empty_like(planes)
     tmp = torch.empty_like(planes) if num_iter > 1 else None
-    _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
-              _lib.int_array(dilations), len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
-              _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off), P, int(max_c), _lib.stream())
+    dil = _lib.int_array(dilations)
+    for b0, b1, mc in segments:
+        _lib.call("excel_par_forward", _lib.ptr(imgs) + b0 * imgs.stride(0) * 4, imgs.stride(0), imgs.stride(1), imgs.stride(2),
+                  b1 - b0, hi, wi, H, W, dil, len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
+                  _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off) + 4 * b0, P, int(mc), _lib.stream())
     return out
 
 

@@ -98,6 +98,9 @@ def test_refine_batch_vs_oracle():
     imgs = synth.images(B, S, seed=9)
     labels, planes, plane_off, refined = affutils.refine_batch(attr.cuda(), attn.cuda(), cls.cuda(), imgs.cuda(),
                                                                PAR(port.PAR_DILATIONS, 20), return_cams=True)
+    # the production path sorts the images by plane count and launches PAR per count class: identical labels
+    labels_sorted = affutils.refine_batch(attr.cuda(), attn.cuda(), cls.cuda(), imgs.cuda(), PAR(port.PAR_DILATIONS, 20))
+    assert torch.equal(labels_sorted, labels)
     labels, planes, off = labels.cpu(), planes.cpu(), plane_off.cpu().tolist()
     for b in range(B):
         lst, cl = port.refine_cams_with_aff(attr[b], attn[:, b], cls[b], (S, S), caa_thre=0.79)
