@@ -24,6 +24,7 @@ SIGNATURES = {
     "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
     "excel_svc_mean_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),
+    "excel_svc_seg_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "excel_svc_sinkhorn": ([_p, _i, _i, _i, _p, _p, _p], _i),
     "excel_svc_build_trans": ([_p, _p, _p, _i, _i, _p, _p], _i),
     "excel_svc_box_mask": ([_p, _i64, _i64, _p, _p, _i, _i, _i, _c.c_double, _p, _p, _p], _i),
@@ -35,6 +36,9 @@ SIGNATURES = {
     "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
     "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p], _i),
     "excel_gemm_tc": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _p], _i),
+    "excel_radius_mask": ([_i, _i, _i, _p, _p], _i),
+    "excel_affinity_label": ([_p, _i, _i, _i, _i, _i, _p, _i64, _p, _p], _i),
+    "excel_lam_to_label": ([_p, _p, _i, _i, _i, _i, _f, _f, _f, _i, _i64, _p, _p, _p], _i),
     "excel_sgemm": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _i, _i64, _i64, _i64, _f, _i, _i, _p], _i),
 }
 

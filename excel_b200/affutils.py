@@ -23,7 +23,7 @@ def _class_lists(cls_labels):
     return [torch.where(row)[0].to(torch.int64) for row in host]
 
 
-def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None):
+def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None, seg_attn=None):
     """attr_maps [B,n_p,K]; attn [L,B,N,N] (arbitrary stride_l / stride_b, rows contiguous).
     Returns refined [Q, n_p] for the Q = sum_b n_b (image, class) pairs, image-major (images in `order`, default
     0..B-1), classes ascending."""
@@ -44,8 +44,14 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, orde
     img_of, cls_of = img_of.to(dev, non_blocking=True), cls_of.to(dev, non_blocking=True)
     st = _lib.stream()
     A = torch.empty((B, n_p, n_p), dtype=torch.float32, device=dev)
-    _lib.call("excel_svc_mean_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), L, B, N, attn_layers,
-              _lib.ptr(A), st)
+    if seg_attn is None:
+        _lib.call("excel_svc_mean_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), L, B, N, attn_layers,
+                  _lib.ptr(A), st)
+    else:   # LVC branch (utils/affutils.py:182-195): seg_attn [B, n_p, n_p]
+        seg = _lib.f32c(seg_attn).reshape(B, n_p, n_p)
+        dws = torch.empty((B * attn_layers,), dtype=torch.float32, device=dev)
+        _lib.call("excel_svc_seg_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), L, B, N, attn_layers,
+                  _lib.ptr(seg), _lib.ptr(dws), _lib.ptr(A), st)
     r = torch.empty((B, n_p), dtype=torch.float32, device=dev)
     c = torch.empty_like(r)
     _lib.call("excel_svc_sinkhorn", _lib.ptr(A), B, n_p, 3, _lib.ptr(r), _lib.ptr(c), st)
@@ -93,11 +99,10 @@ def box_masks(attr_maps, cls_lists, gh, gw, caa_thre):
 def refine_cams_with_aff(attr_map, attn_weights, cls_label, size, caa_thre=0.79, attn_layers=6, seg_attn=None):
     """Same contract as utils/affutils.py:177-223: returns (list of n [h//16, w//16] CUDA tensors,
     int64 class indices on the CPU)."""
-    if seg_attn is not None:
-        raise NotImplementedError("excel_b200: the seg_attn (LVC) branch of refine_cams_with_aff is SURVEY §8(f1), not built yet")
     h, w = size
     cls_lst = torch.where(cls_label)[0].detach().cpu()
-    out = _svc_vectors(attr_map.unsqueeze(0), attn_weights.unsqueeze(1), [cls_lst], h // 16, w // 16, caa_thre, attn_layers)
+    out = _svc_vectors(attr_map.unsqueeze(0), attn_weights.unsqueeze(1), [cls_lst], h // 16, w // 16, caa_thre, attn_layers,
+                       seg_attn=seg_attn)
     return [o.view(h // 16, w // 16) for o in out], cls_lst
 
 

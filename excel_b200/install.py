@@ -4,7 +4,7 @@ engine/validatation_engine.py) run on the sm_100a hot path WITHOUT editing them.
 The reference has no plugin API; its boundary is a set of module-level Python functions imported by name
 (SURVEY.md §8b).  ``install()`` imports those reference modules and rebinds the hot-path symbols to this
 package's implementations, so that a later ``from utils.affutils import refine_cams_with_aff`` in a script binds
-ours.  Branches this round has not built (the LVC ``ex_feats`` / ``seg_attn`` paths) keep
+ours.  The one branch this round has not built (the LVC ``ex_feats`` path of the encoder) keeps
 dispatching to the reference's own PyTorch code.
 
     python -m excel_b200.run tools/infer_lam.py --infer_set train --training_free true ...
@@ -29,20 +29,15 @@ def install(reference_root=None):
         originals[module_name + "." + attr] = getattr(mod, attr)
         setattr(mod, attr, new)
 
-    ref_aff = importlib.import_module("utils.affutils")
-    ref_refine = ref_aff.refine_cams_with_aff
-
-    def refine_cams_with_aff(attr_map, attn_weights, cls_label, size, caa_thre=0.79, attn_layers=6, seg_attn=None):
-        if seg_attn is not None:      # LVC branch: reference implementation
-            return ref_refine(attr_map, attn_weights, cls_label, size, caa_thre, attn_layers, seg_attn)
-        return my_aff.refine_cams_with_aff(attr_map, attn_weights, cls_label, size, caa_thre, attn_layers)
-
-    patch("utils.affutils", "refine_cams_with_aff", refine_cams_with_aff)
+    patch("utils.affutils", "refine_cams_with_aff", my_aff.refine_cams_with_aff)
     patch("utils.affutils", "refine_cams_with_bkg_weclip", my_aff.refine_cams_with_bkg_weclip)
     patch("utils.affutils", "compute_trans_mat", my_aff.compute_trans_mat)
     patch("utils.PAR", "PAR", my_par.PAR)
     patch("utils.camutils", "cure_attr_map", my_cam.cure_attr_map)
     patch("utils.camutils", "cure_attr_map_flip", my_cam.cure_attr_map_flip)
+    patch("utils.camutils", "lam_to_label", my_cam.lam_to_label)
+    patch("utils.camutils", "cams_to_affinity_label", my_cam.cams_to_affinity_label)
+    patch("utils.camutils", "get_mask_by_radius", my_cam.get_mask_by_radius)
 
     ref_clip = importlib.import_module("clip")
     ref_clip_inner = importlib.import_module("clip.clip")

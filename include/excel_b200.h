@@ -62,6 +62,12 @@ int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_
 int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N,
                              int attn_layers, float* A, void* stream);
 
+/* utils/affutils.py:182-195 (the seg_attn / LVC branch of refine_cams_with_aff): per image keep the layers l of the
+ * last `attn_layers` whose sum(seg_attn - attn_l[1:,1:]) is <= the mean over those layers;
+ * A = (sum of kept layers) / (number kept + 1e-5) * seg_attn.  seg_attn [B,N-1,N-1]; diff_ws [B*attn_layers]. */
+int excel_svc_seg_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N, int attn_layers,
+                            const float* seg_attn, float* diff_ws, float* A, void* stream);
+
 /* utils/affutils.py:11-16 (compute_trans_mat, the 1 + 2 rounds of column / row normalisation) in scaling
  * form: trans = diag(r) A diag(c).  A [B,np,np]; r, c [B,np] outputs. rounds = 3 in the reference. */
 int excel_svc_sinkhorn(const float* A, int B, int np, int rounds, float* r, float* c, void* stream);
@@ -143,6 +149,23 @@ int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_st
  * 0 <= t < nc (other labels, e.g. 255 = ignore, are skipped).  hist: int64 [nc*nc], NOT cleared here. */
 int excel_confusion_hist(const int64_t* label_true, const int64_t* label_pred, int64_t n, int num_classes,
                          int64_t* hist, void* stream);
+
+/* ---------------------------------------------------------------- label utilities (utils/camutils.py) */
+
+/* utils/camutils.py:459-476 (get_mask_by_radius): mask [h*w, h*w] fp32, 1 where both |dy|,|dx| <= radius. */
+int excel_radius_mask(int h, int w, int radius, float* mask, void* stream);
+
+/* utils/camutils.py:438-457 (cams_to_affinity_label): label [B,H,W] int64 -> out [B, gh*gw, gh*gw] int64
+ * (1 same label, 0 different, ignore_index where a label is ignore_index or mask[i,j] == 0; mask may be NULL);
+ * the label map is down-sampled to gh x gw with nearest-neighbour (F.interpolate) semantics. */
+int excel_affinity_label(const int64_t* label, int B, int H, int W, int gh, int gw, const float* mask,
+                         int64_t ignore_index, int64_t* out, void* stream);
+
+/* utils/camutils.py:123-143 (lam_to_label, img_box=None): valid_cam = cls*cam [B,C,H,W]; label [B,H,W] int64 =
+ * argmax_c + 1 with the bkg / high / low thresholds applied. */
+int excel_lam_to_label(const float* cam, const float* cls_label, int B, int C, int H, int W, float bkg_thre,
+                       float high_thre, float low_thre, int ignore_mid, int64_t ignore_index, float* valid_cam,
+                       int64_t* label, void* stream);
 
 /* ---------------------------------------------------------------- dense fp32 GEMM ------------- */
 

@@ -125,6 +125,18 @@ def main():
     np.savez(os.path.join(OUT, "vit_tiny.npz"), tok=tok.numpy(), attn=attn.numpy(), feats=feats.numpy(),
              attr_maps=attr_maps.numpy(), labels=np.stack(labels), cams=np.stack(cams_all),
              chk_w=checksum(*[v for k, v in W.items() if k != "meta"]), chk_img=checksum(imgs), chk_text=checksum(text))
+    # ---- training-side label utilities (utils/camutils.py:123-143, 438-476)
+    m_ref = ref.camutils.get_mask_by_radius(h=6, w=7, radius=2)
+    g2 = torch.Generator().manual_seed(77)
+    lab = torch.randint(0, 4, (2, 96, 112), generator=g2)
+    lab[0, :20] = 255
+    a_ref = ref.camutils.cams_to_affinity_label(lab.clone(), mask=m_ref, ignore_index=255)
+    cam2 = torch.rand(2, 5, 24, 28, generator=g2)
+    cls3 = (torch.rand(2, 5, generator=g2) > 0.4).float()
+    v_ref, l_ref = ref.camutils.lam_to_label(cam2, cls3, bkg_thre=0.45, high_thre=0.6, low_thre=0.3, ignore_mid=True, ignore_index=255)
+    _, l2_ref = ref.camutils.lam_to_label(cam2, cls3, bkg_thre=0.45)
+    np.savez(os.path.join(OUT, "labels.npz"), mask=m_ref, lab=lab.numpy(), aff=a_ref.numpy(), cam=cam2.numpy(), cls=cls3.numpy(),
+             l_mid=l_ref.numpy(), l_bkg=l2_ref.numpy(), valid=v_ref.numpy())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 

@@ -405,3 +405,39 @@ def miou_from_hist(hist):
     with np.errstate(divide="ignore", invalid="ignore"):
         iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
     return float(np.nanmean(iu[hist.sum(1) > 0]))
+
+
+# --------------------------------------------------------------------------- label utilities (f2)
+
+
+def get_mask_by_radius(h, w, radius):
+    """utils/camutils.py:459-476 without the Python double loop."""
+    ys, xs = np.divmod(np.arange(h * w), w)
+    return ((np.abs(ys[:, None] - ys[None]) <= radius) & (np.abs(xs[:, None] - xs[None]) <= radius)).astype(np.float64)
+
+
+def cams_to_affinity_label(cam_label, mask=None, ignore_index=255):
+    """utils/camutils.py:438-457."""
+    b, h, w = cam_label.shape
+    small = F.interpolate(cam_label.unsqueeze(1).float(), size=[h // 16, w // 16], mode="nearest").reshape(b, 1, -1)
+    rep = small.repeat([1, small.shape[-1], 1])
+    aff = (rep == rep.permute(0, 2, 1)).long()
+    for i in range(b):
+        if mask is not None:
+            aff[i, torch.as_tensor(mask) == 0] = ignore_index
+        aff[i, :, rep[i, 0, :] == ignore_index] = ignore_index
+        aff[i, rep[i, 0, :] == ignore_index, :] = ignore_index
+    return aff
+
+
+def lam_to_label(cam, cls_label, bkg_thre=0.5, high_thre=None, low_thre=None, ignore_mid=False, ignore_index=None):
+    """utils/camutils.py:123-143 (img_box=None)."""
+    valid = cls_label[:, :, None, None] * cam
+    val, lab = valid.max(dim=1)
+    lab = lab + 1
+    if ignore_mid:
+        lab[val <= high_thre] = ignore_index
+        lab[val <= low_thre] = 0
+    else:
+        lab[val <= bkg_thre] = 0
+    return valid, lab

@@ -41,8 +41,11 @@ def test_trans_mat_and_refine_golden(golden):
     assert np.array_equal(cl.numpy(), G["cls_lst"]) and not cl.is_cuda
     out = torch.stack(lst).cpu()
     assert ((out - t(G["refined"])).abs() / t(G["refined"]).abs().clamp_min(1e-6)).max() < 1e-4
-    with pytest.raises(NotImplementedError):
-        affutils.refine_cams_with_aff(t(G["attr"]).cuda(), A.cuda(), t(G["cls"]).cuda(), (128, 128), seg_attn=t(G["seg_attn"]).cuda())
+    # seg_attn (LVC) branch, utils/affutils.py:182-195, caa_thre 0.75 as in engine/validatation_engine.py:33
+    lst, _ = affutils.refine_cams_with_aff(t(G["attr"]).cuda(), A.cuda(), t(G["cls"]).cuda(), (128, 128), caa_thre=0.75,
+                                           seg_attn=t(G["seg_attn"]).cuda())
+    out = torch.stack(lst).cpu()
+    assert ((out - t(G["refined_seg"])).abs() / t(G["refined_seg"]).abs().clamp_min(1e-6)).max() < 1e-4
 
 
 def test_bkg_weclip_golden(golden):
@@ -110,3 +113,21 @@ def test_refine_batch_vs_oracle():
         top2 = ref_planes.topk(2, dim=0).values
         margin = (top2[0] - top2[1]) / top2[0].abs()
         assert int(mism.sum()) <= 8 and not bool((mism & (margin > 1e-4)).any()), (b, int(mism.sum()))
+
+
+def test_label_utils_golden(golden):
+    """utils/camutils.py:123-143,438-476 on the device vs the reference fixtures (integer outputs: bit-exact)."""
+    from excel_b200 import camutils
+    G = golden("labels")
+    mask = camutils.get_mask_by_radius(6, 7, 2)
+    assert np.array_equal(mask.cpu().numpy().astype(np.float64), G["mask"])
+    aff = camutils.cams_to_affinity_label(t(G["lab"]).cuda(), mask=mask, ignore_index=255)
+    assert np.array_equal(aff.cpu().numpy(), G["aff"])
+    assert np.array_equal(camutils.cams_to_affinity_label(t(G["lab"]).cuda(), mask=G["mask"], ignore_index=255).cpu().numpy(), G["aff"])
+    v, l = camutils.lam_to_label(t(G["cam"]).cuda(), t(G["cls"]).cuda(), bkg_thre=0.45, high_thre=0.6, low_thre=0.3, ignore_mid=True,
+                                 ignore_index=255)
+    assert np.array_equal(l.cpu().numpy(), G["l_mid"]) and np.array_equal(v.cpu().numpy(), G["valid"])
+    _, l2 = camutils.lam_to_label(t(G["cam"]).cuda(), t(G["cls"]).cuda(), bkg_thre=0.45)
+    assert np.array_equal(l2.cpu().numpy(), G["l_bkg"])
+    big = camutils.get_mask_by_radius(32, 32, 8).cpu().numpy()
+    assert np.array_equal(big.astype(np.float64), port.get_mask_by_radius(32, 32, 8))

@@ -79,3 +79,12 @@ def test_vit_tiny_golden(golden):
         lab, cams, _ = port.refine_cams_with_bkg_weclip(lst, imgs[i], cl, (96, 96))
         assert (cams - t(G["cams"][i])).abs().max() < 1e-6
         assert np.array_equal(lab.numpy().astype(np.int16), G["labels"][i])
+
+
+def test_label_utils_golden(golden):
+    G = golden("labels")
+    assert np.array_equal(port.get_mask_by_radius(6, 7, 2), G["mask"])
+    assert np.array_equal(port.cams_to_affinity_label(t(G["lab"]), G["mask"], 255).numpy(), G["aff"])
+    v, l = port.lam_to_label(t(G["cam"]), t(G["cls"]), 0.45, 0.6, 0.3, True, 255)
+    assert np.array_equal(l.numpy(), G["l_mid"]) and np.array_equal(v.numpy(), G["valid"])
+    assert np.array_equal(port.lam_to_label(t(G["cam"]), t(G["cls"]), 0.45)[1].numpy(), G["l_bkg"])
