@@ -21,12 +21,12 @@
 namespace xl {
 
 constexpr int kABK = 64;                                  // head dim == one 64-wide k block
-constexpr int kAStages = 2;
+constexpr int kAStages = 3;                               // the kernels are TMA-latency bound: 128 KB in flight per SM
 constexpr uint32_t kATile = 128 * kABK * 2;               // 16 KB: one 128-row fp16 operand tile
 constexpr uint32_t kAStage = 4 * kATile;                  // X_hi, X_lo, Y_hi, Y_lo
-constexpr uint32_t kAEpi = 4 * 16384;                     // 2 teams x 2 TMA-store staging buffers
+constexpr uint32_t kAEpi = 2 * 16384;                     // one TMA-store staging buffer per epilogue team (+1 KB spill-over)
 constexpr int kAThreads = 64 + 256;
-constexpr size_t kASmem = kAStages * kAStage + kAEpi + 2048 /*row stats exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t kASmem = kAStages * kAStage + kAEpi + 1024 /*row stats exchange / staging tail*/ + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float kProbScaleA = 1024.f;                     // 2^10; must match vit.cu: kProbScale
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -41,8 +41,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ebuf = tiles + kAStages * kAStage;
-    float* xch = reinterpret_cast<float*>(ebuf + kAEpi);  // [2][128] (m, l) of the second column half
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ebuf + kAEpi + 2048);
+    float* xch = reinterpret_cast<float*>(ebuf + kAEpi);  // [2][128] (m, l) of the second column half (stats mode)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ebuf + kAEpi + 1024);
     uint64_t* empty_bar = full_bar + kAStages;
     uint64_t* acc_full = empty_bar + kAStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -132,7 +132,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int trow = lg * 32 + lane;
         const int team_bar = 1 + half;
         const bool leader = (ew & 3) == 0 && lane == 0;           // first warp of the team
-        uint8_t* tbuf = ebuf + half * 2 * 16384;
+        uint8_t* tbuf = ebuf + half * 16384;
         int it = 0, ck = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             int b, h, rb, kb;
@@ -171,34 +171,50 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const int key0 = kb * 128 + c * 32;
                     const bool full = key0 + 32 <= p.N;   // (uniform) no key of this chunk is padding
                     if (MODE == 0) {
-                        // running row max / sum in the exp2 domain; alpha > 0, so max(alpha*a) = alpha*max(a)
-                        float cmax = -INFINITY;
+                        // running row max / sum in the exp2 domain; alpha > 0, so max(alpha*a) = alpha*max(a).
+                        // Four independent max / sum chains keep the FMNMX / FADD latency off the critical path.
+                        if (!full) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (full || key0 + e < p.N) cmax = fmaxf(cmax, __uint_as_float(r[e]));
-                        const float m_new = fmaxf(m_run, p.alpha * cmax);
+                            for (int e = 0; e < 32; ++e)
+                                if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf: padding keys drop out of max and sum
+                        }
+                        float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            c0 = fmaxf(c0, __uint_as_float(r[e]));
+                            c1 = fmaxf(c1, __uint_as_float(r[e + 1]));
+                            c2 = fmaxf(c2, __uint_as_float(r[e + 2]));
+                            c3 = fmaxf(c3, __uint_as_float(r[e + 3]));
+                        }
+                        const float m_new = fmaxf(m_run, p.alpha * fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
                         if (m_new > -INFINITY) {
-                            float sum = 0.f;
+                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                            for (int e = 0; e < 32; ++e) {
-                                const float ex = ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_new));
-                                sum += (full || key0 + e < p.N) ? ex : 0.f;
+                            for (int e = 0; e < 32; e += 4) {
+                                s0 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_new));
+                                s1 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 1]), -m_new));
+                                s2 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 2]), -m_new));
+                                s3 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 3]), -m_new));
                             }
-                            l_run = l_run * ex2_approx(m_run - m_new) + sum;
+                            l_run = l_run * ex2_approx(m_run - m_new) + ((s0 + s1) + (s2 + s3));
                             m_run = m_new;
                         }
                     } else {
                         // pr = 2^10 * p = exp2(alpha*s - (m + log2 l - 10)): one FFMA + one MUFU per element
                         float pr[32];
+                        if (!full) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
+                        }
 #pragma unroll
                         for (int e = 0; e < 32; ++e) {
-                            const float v = ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_row));
-                            pr[e] = (full || key0 + e < p.N) ? v : 0.f;
+                            pr[e] = ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_row));
                             acc[cc][e] += pr[e];
                         }
                         if (p.write_p && key0 < p.np) {  // (uniform) P operand tile: split fp16, scaled, via TMA store
-                            uint8_t* sb = tbuf + (ck & 1) * 16384;
-                            if (leader) tma_store_wait_read<1>();
+                            uint8_t* sb = tbuf;
+                            if (leader) tma_store_wait_read<0>();   // the previous store has finished reading the buffer
                             bar_sync(team_bar, 128);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -242,7 +258,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 bar_sync(3, 256);
             } else {
                 // head-reduced map out[b,row,key] = coef * sum p: staged per 32-column chunk in the team's buffer
-                // (pitch 33 floats) and written with 8 lanes per row segment -> 128 B coalesced stores
+                // and written with 8 lanes per row segment -> 128 B coalesced stores
                 float* stg = reinterpret_cast<float*>(tbuf);
                 const int tid = (ew & 3) * 32 + lane, sub = tid >> 3, c4 = (tid & 7) * 4;
 #pragma unroll
@@ -252,7 +268,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if (leader) tma_store_wait_read<0>();  // P stores may still be reading the staging buffers
                     bar_sync(team_bar, 128);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) stg[trow * 33 + e] = (p.coef * (1.f / kProbScaleA)) * acc[cc][e];
+                    for (int e = 0; e < 32; ++e)   // row-rotated columns: conflict-free without padding (16 KB exactly)
+                        stg[trow * 32 + ((e + trow) & 31)] = (p.coef * (1.f / kProbScaleA)) * acc[cc][e];
                     bar_sync(team_bar, 128);
                     for (int rr = sub; rr < 128; rr += 16) {
                         const int orow = rb * 128 + rr;
@@ -260,7 +277,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         float* o = p.out + ((int64_t)b * p.N + orow) * p.N + key0 + c4;
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (key0 + c4 + e < p.N) o[e] = stg[rr * 33 + c4 + e];
+                            if (key0 + c4 + e < p.N) o[e] = stg[rr * 32 + ((c4 + e + rr) & 31)];
                     }
                 }
                 bar_sync(team_bar, 128);  // staging buffers are reused by the next item's P tiles

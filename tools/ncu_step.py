@@ -8,7 +8,7 @@ from excel_b200.pipeline import ExCELHotPath
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 hp = ExCELHotPath(SurgeryViT(synth.random_visual_weights(seed=0)), synth.text_bank(45, 512, seed=1), 20)
-imgs = synth.images(B, S, seed=10).cuda(); cls = synth.class_labels(B, 20, seed=110, n_fixed=3).cuda()
+imgs = synth.images(B, S, seed=10).cuda(); cls = synth.class_labels(B, 20, seed=110, n_fixed=None).cuda()
 for _ in range(2):
     hp(imgs, cls)
 torch.cuda.synchronize()
