@@ -151,9 +151,9 @@ def _segments(counts):
 
 
 def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=None, caa_thre=0.79, attn_layers=6,
-                 return_cams=False):
+                 return_cams=False, cls_lists=None):
     """Fused batched SVC + PAR + argmax (tools/infer_lam.py:88-94 for the whole batch).
-    attr_maps [B,n_p,K], attn_weights [L,B,N,N], cls_labels [B,K], par_imgs [B,3,h,w].
+    attr_maps [B,n_p,K], attn_weights [L,B,N,N], cls_labels [B,K] (any device), par_imgs [B,3,h,w].
     Returns labels [B,H,W] int64 (and the packed planes, plane_off, refined CAMs when return_cams).
 
     Images are processed in order of their plane count so that PAR launches run the kernel variant that fits
@@ -162,7 +162,8 @@ def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=No
     h, w = par_imgs.shape[-2:]
     H, W = (h, w) if out_size is None else (int(out_size[0]), int(out_size[1]))
     gh, gw = h // 16, w // 16
-    cls_lists = _class_lists(cls_labels)
+    # host-side class lists: pass `cls_lists` (or CPU labels) to keep the device stream free of a D2H sync here
+    cls_lists = _class_lists(cls_labels) if cls_lists is None else cls_lists
     counts = [int(c.numel()) for c in cls_lists]
     if min(counts) == 0:
         raise RuntimeError("stack expects a non-empty TensorList")  # an image without classes (affutils.py:63)

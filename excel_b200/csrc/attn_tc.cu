@@ -25,7 +25,10 @@ constexpr int kAStages = 3;                               // the kernels are TMA
 constexpr uint32_t kATile = 128 * kABK * 2;               // 16 KB: one 128-row fp16 operand tile
 constexpr uint32_t kAStage = 4 * kATile;                  // X_hi, X_lo, Y_hi, Y_lo
 constexpr uint32_t kAEpi = 2 * 16384;                     // one TMA-store staging buffer per epilogue team (+1 KB spill-over)
-constexpr int kAThreads = 64 + 256;
+// stats pass: 16 epilogue warps (four per TMEM lane group, 32 columns each) hide the MUFU / FMNMX latency chains;
+// probs pass: 8 (two per lane group, 64 columns each -- its epilogue carries 64 head-sum accumulators per thread)
+__host__ __device__ constexpr int attn_epi_warps(int mode) { return mode == 0 ? 16 : 8; }
+__host__ __device__ constexpr int attn_threads(int mode) { return 64 + 32 * attn_epi_warps(mode); }
 constexpr size_t kASmem = kAStages * kAStage + kAEpi + 1024 /*row stats exchange / staging tail*/ + 1024 /*align*/ + 256 /*barriers*/;
 constexpr float kProbScaleA = 1024.f;                     // 2^10; must match vit.cu: kProbScale
 
@@ -36,12 +39,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kAThreads, 1)
+__global__ void __launch_bounds__(attn_threads(MODE), 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmP, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ebuf = tiles + kAStages * kAStage;
-    float* xch = reinterpret_cast<float*>(ebuf + kAEpi);  // [2][128] (m, l) of the second column half (stats mode)
+    float* xch = reinterpret_cast<float*>(ebuf);          // stats mode: [NPART-1][2][128] (m, l) of the other column parts
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ebuf + kAEpi + 1024);
     uint64_t* empty_bar = full_bar + kAStages;
     uint64_t* acc_full = empty_bar + kAStages;
@@ -62,7 +65,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 8);  // one arrival per epilogue warp
+            mbar_init(&acc_empty[s], attn_epi_warps(MODE));  // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -127,8 +130,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
         }
     } else {
-        // ---- epilogue: warp (lg, half): TMEM lanes 32*lg..+31 (rows), columns 64*half..+63 of every S tile
-        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;   // warps 2..5 -> half 0, 6..9 -> half 1 (lane group = warp % 4)
+        // ---- epilogue: warp (lg, half): TMEM lanes 32*lg..+31 (rows), columns 32*CPW*half..+32*CPW-1 of every S tile
+        constexpr int NPART = attn_epi_warps(MODE) / 4, CPW = 4 / NPART;   // column parts; 32-column chunks per warp
+        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;   // part = ew / 4 (lane group = warp % 4)
         const int trow = lg * 32 + lane;
         const int team_bar = 1 + half;
         const bool leader = (ew & 3) == 0 && lane == 0;           // first warp of the team
@@ -147,23 +151,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
                     for (int e = 0; e < 32; ++e) acc[cc][e] = 0.f;
             }
+            float m_next = INFINITY;   // rows past N: exp2(-inf) = 0
+            if (MODE == 1 && row_ok) m_next = __ldg(p.m + ((int64_t)b * p.H) * p.N + row);   // (type 0, head 0)
             for (int j = 0; j < inner; ++j, ++it) {
                 decode(item, j, b, h, rb, kb);
                 const int buf = it & 1;
-                float m_row = INFINITY;   // rows past N: exp2(-inf) = 0
-                if (MODE == 1 && row_ok) {
-                    const int ty = h / p.H, hd = h - ty * p.H;
-                    const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
-                    m_row = __ldg(p.m + si) + __log2f(__ldg(p.l + si)) - 10.f;   // folds 1/l and the 2^10 operand scale
+                // m_row = m + log2(l) - 10 (stats pass): folds 1/l and the 2^10 operand scale.  The value for the NEXT
+                // tile is fetched before this tile's wait so that the global-load latency stays off the critical path.
+                const float m_row = m_next;
+                if (MODE == 1 && row_ok && j + 1 < inner) {
+                    const int hn = j + 1, ty = hn / p.H, hd = hn - ty * p.H;
+                    m_next = __ldg(p.m + (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row);
                 }
                 mbar_wait(&acc_full[buf], (it >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = half * 2 + cc;
+                for (int cc = 0; cc < CPW; ++cc) {
+                    const int c = half * CPW + cc;
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + c * 32), r);
-                    if (cc == 1) {  // this warp's TMEM reads of the tile are done
+                    if (cc == CPW - 1) {  // this warp's TMEM reads of the tile are done
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -243,19 +250,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
             if (MODE == 0) {
-                // merge the two column halves of each row, write m, l
-                if (half == 1) { xch[trow] = m_run; xch[128 + trow] = l_run; }
-                bar_sync(3, 256);
+                // merge the column parts of each row; write m + log2(l) - 10 (what the probs pass subtracts)
+                if (half > 0) { xch[(half - 1) * 256 + trow] = m_run; xch[(half - 1) * 256 + 128 + trow] = l_run; }
+                bar_sync(3, 32 * attn_epi_warps(MODE));
                 if (half == 0 && row_ok) {
-                    const float m1 = xch[trow], l1 = xch[128 + trow];
-                    const float mf = fmaxf(m_run, m1);
-                    const float lf = l_run * ex2_approx(m_run - mf) + l1 * ex2_approx(m1 - mf);
+                    float mf = m_run;
+#pragma unroll
+                    for (int q = 0; q < NPART - 1; ++q) mf = fmaxf(mf, xch[q * 256 + trow]);
+                    float lf = l_run * ex2_approx(m_run - mf);
+#pragma unroll
+                    for (int q = 0; q < NPART - 1; ++q) lf += xch[q * 256 + 128 + trow] * ex2_approx(xch[q * 256 + trow] - mf);
                     const int ty = h / p.H, hd = h - ty * p.H;
-                    const int64_t si = (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row;
-                    p.m[si] = mf;
-                    p.l[si] = lf;
+                    p.m[(((int64_t)ty * p.B + b) * p.H + hd) * p.N + row] = mf + __log2f(lf) - 10.f;
                 }
-                bar_sync(3, 256);
+                bar_sync(3, 32 * attn_epi_warps(MODE));
             } else {
                 // head-reduced map out[b,row,key] = coef * sum p: staged per 32-column chunk in the team's buffer
                 // and written with 8 lanes per row segment -> 128 B coalesced stores
@@ -302,7 +310,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.ntypes >= 1 && p.ntypes <= 3 &&
                    (!p.write_p || p.ntypes == 1), "attn_scores: bad shape");
-    XL_REQUIRE(p.m && p.l && p.out, "attn_scores: missing buffers");
+    XL_REQUIRE(p.m && p.out, "attn_scores: missing buffers");
     const int nblk = (p.N + 127) / 128;
     CUtensorMap tmP = tmQ;
     if (p.write_p) {
@@ -314,9 +322,9 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
             return e;
     }
     const int items0 = p.B * p.ntypes * p.H * nblk, items1 = p.B * nblk * nblk;
-    attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);
+    attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, attn_threads(0), kASmem, st>>>(tmQ, tmP, p);
     if (int e = check_launch("attn_tc_kernel<stats>")) return e;
-    attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmP, p);
+    attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, attn_threads(1), kASmem, st>>>(tmQ, tmP, p);
     return check_launch("attn_tc_kernel<probs>");
 }
 

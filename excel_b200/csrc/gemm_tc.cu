@@ -174,7 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float x = alpha * __uint_as_float(r[j]);
                         if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
                         // QuickGELU x * sigmoid(1.702 x) (clip_surgery_model.py:280-282), exp2 domain
-                        if (act == 1) x = x * __frcp_rn(1.f + exp2f(-2.4554669595930156f * x));
+                        if (act == 1) x = __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x));
                         v[j] = x;
                     }
                     if (p.C) {
@@ -258,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 4; ++e) {
                         float x = alpha * __uint_as_float(r[j + e]);
                         if (bias && nb + j + e < p.N) x += __ldg(bias + nb + j + e);
-                        if (act == 1) x = x * __frcp_rn(1.f + exp2f(-2.4554669595930156f * x));  // QuickGELU
+                        if (act == 1) x = __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x));  // QuickGELU
                         v[e] = x;
                     }
                     *reinterpret_cast<float4*>(stage + trow * kPitch + j) = make_float4(v[0], v[1], v[2], v[3]);

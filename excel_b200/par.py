@@ -16,10 +16,22 @@ def _pitch(w):
     return (w + 3) & ~3
 
 
+_SIDE = {}
+
+
+def _side_streams(dev, n):
+    """n reusable side streams of device `dev` (created once)."""
+    pool = _SIDE.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
 def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2, segments=None):
     """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
     segments: optional [(b0, b1, max planes per image)] runs of consecutive images launched separately (so that each
     run gets the kernel variant matching its plane count).  Returns the refined planes [P,H,W] (a new tensor)."""
+    _lib.ptr(imgs), _lib.ptr(planes)   # CUDA tensors only: raises for CPU inputs (no fallback)
     imgs = imgs.float()
     if imgs.stride(-1) != 1:
         imgs = imgs.contiguous()
@@ -30,18 +42,29 @@ def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group
         return planes.clone()
     K = 8 * len(dilations)
     segments = [(0, B, int(max_c))] if not segments else segments
-    nmax = max(b1 - b0 for b0, b1, _ in segments)
-    g = nmax if group <= 0 else min(group, nmax)
     dev = planes.device
-    aff = torch.empty((g, K, H, _pitch(W)), dtype=torch.float32, device=dev)   # internal layout: row pitch % 4 == 0
-    rs = torch.empty((nmax, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
     out = torch.empty_like(planes)
     tmp = torch.empty_like(planes) if num_iter > 1 else None
     dil = _lib.int_array(dilations)
-    for b0, b1, mc in segments:
-        _lib.call("excel_par_forward", _lib.ptr(imgs) + b0 * imgs.stride(0) * 4, imgs.stride(0), imgs.stride(1), imgs.stride(2),
-                  b1 - b0, hi, wi, H, W, dil, len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
-                  _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off) + 4 * b0, P, int(mc), _lib.stream())
+    # The runs touch disjoint images and planes: each gets its own affinity workspace and (beyond the first) its own
+    # side stream, forked from / joined to the caller's stream with events, so that the short launches of a small run
+    # fill the tail of a large one instead of queueing behind it.
+    cur = torch.cuda.current_stream(dev)
+    side = _side_streams(dev, len(segments) - 1)
+    for i, (b0, b1, mc) in enumerate(segments):
+        nb = b1 - b0
+        g = nb if group <= 0 else min(group, nb)
+        st = cur if i == 0 else side[i - 1]
+        if st is not cur:
+            st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            aff = torch.empty((g, K, H, _pitch(W)), dtype=torch.float32, device=dev)   # internal layout: row pitch % 4 == 0
+            rs = torch.empty((nb, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
+            _lib.call("excel_par_forward", _lib.ptr(imgs) + b0 * imgs.stride(0) * 4, imgs.stride(0), imgs.stride(1),
+                      imgs.stride(2), nb, hi, wi, H, W, dil, len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
+                      _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off) + 4 * b0, P, int(mc), _lib.stream())
+    for st in side[:len(segments) - 1]:
+        cur.wait_stream(st)
     return out
 
 

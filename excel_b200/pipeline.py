@@ -32,7 +32,88 @@ class ExCELHotPath:
 
     @torch.no_grad()
     def __call__(self, imgs, cls_labels, par_imgs=None, out_size=None):
-        """imgs [B,3,S,S] (normalised), cls_labels [B,num_fg] one-hot -> labels [B,H,W] int64."""
+        """imgs [B,3,S,S] (normalised), cls_labels [B,num_fg] one-hot (CPU or CUDA) -> labels [B,H,W] int64.
+        The image-level labels steer host logic (which planes exist), so they are read on the host BEFORE the
+        encoder is enqueued: with CPU labels the device stream never waits on the host inside a step."""
+        cls_lists = affutils._class_lists(cls_labels)
         attr, attn, _ = self.cams(imgs)
         par_imgs = imgs if par_imgs is None else par_imgs
-        return affutils.refine_batch(attr, attn, cls_labels, par_imgs, self.par, out_size, self.caa_thre)
+        return affutils.refine_batch(attr, attn, cls_labels, par_imgs, self.par, out_size, self.caa_thre, cls_lists=cls_lists)
+
+
+class HostPipeline:
+    """End-to-end driver for batches that live in HOST memory: `submit(imgs_host, cls_host)` enqueues the H2D copy of
+    the batch on a copy stream, the hot path on the compute stream and the D2H copy of the int64 labels on a second copy
+    stream, and returns the PREVIOUS batch's labels (pinned host tensor, complete) -- so the copies of batch i+1 / i-1
+    overlap the kernels of batch i (a returned tensor stays valid for the next depth-2 submits).  `flush()` returns the
+    last batch's labels.  (The reference moves each image
+    with a blocking `.cuda()` / `.cpu()`, tools/infer_lam.py:76-77,113-114.)"""
+
+    def __init__(self, hot_path, depth=3):
+        self.hp = hot_path
+        self.dev = hot_path.encoder.device
+        self.depth = depth
+        self.s_in = torch.cuda.Stream(device=self.dev)
+        self.s_out = torch.cuda.Stream(device=self.dev)
+        self.slots = [None] * depth      # per slot: device image buffer, pinned label buffer, events
+        self.i = 0
+        self.pending = None              # (pinned labels, done event) of the previous batch
+        self.staged = None               # (slot, ready event, cls_host) of a batch whose H2D copy is already enqueued
+
+    def _slot(self, k, imgs_host, B, H, W):
+        s = self.slots[k]
+        if s is None or s["img"].shape != imgs_host.shape:
+            s = {"img": torch.empty(imgs_host.shape, dtype=torch.float32, device=self.dev),
+                 "lab": torch.empty((B, H, W), dtype=torch.int64).pin_memory(),
+                 "free": None, "lab_free": None}
+            self.slots[k] = s
+        return s
+
+    def stage(self, imgs_host, cls_host):
+        """Enqueue the H2D copy of the NEXT batch (call before `submit` of the current one to overlap them)."""
+        k = self.i % self.depth
+        B, _, H, W = imgs_host.shape
+        s = self._slot(k, imgs_host, B, H, W)
+        if s["free"] is not None:
+            self.s_in.wait_event(s["free"])          # the compute that last read this buffer has finished
+        with torch.cuda.stream(self.s_in):
+            s["img"].copy_(imgs_host, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self.s_in)
+        self.staged = (k, ready, cls_host)
+        self.i += 1
+
+    def submit(self, imgs_host=None, cls_host=None, stage_next=None):
+        """Run the batch staged earlier (or `imgs_host, cls_host` now).  `stage_next=(imgs, cls)` enqueues the next
+        batch's H2D copy before this batch's kernels.  Returns the previous batch's labels (or None)."""
+        if self.staged is None:
+            self.stage(imgs_host, cls_host)
+        k, ready, cls = self.staged
+        self.staged = None
+        s = self.slots[k]
+        if stage_next is not None:
+            self.stage(*stage_next)
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ready)
+        labels = self.hp(s["img"], cls)
+        s["free"] = torch.cuda.Event()
+        s["free"].record(cur)
+        done = torch.cuda.Event()
+        self.s_out.wait_event(s["free"])
+        labels.record_stream(self.s_out)
+        with torch.cuda.stream(self.s_out):
+            s["lab"].copy_(labels, non_blocking=True)
+            done.record(self.s_out)
+        prev = self.pending
+        self.pending = (s["lab"], done)
+        if prev is not None:
+            prev[1].synchronize()
+            return prev[0]
+        return None
+
+    def flush(self):
+        prev, self.pending = self.pending, None
+        if prev is None:
+            return None
+        prev[1].synchronize()
+        return prev[0]
