@@ -301,7 +301,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 }
 
-int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st) {
+int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st, bool stats_only) {
     static bool attr_set = false;
     if (!attr_set) {
         XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
@@ -310,7 +310,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.ntypes >= 1 && p.ntypes <= 3 &&
                    (!p.write_p || p.ntypes == 1), "attn_scores: bad shape");
-    XL_REQUIRE(p.m && p.out, "attn_scores: missing buffers");
+    XL_REQUIRE(p.m && (p.out || stats_only), "attn_scores: missing buffers");
     const int nblk = (p.N + 127) / 128;
     CUtensorMap tmP = tmQ;
     if (p.write_p) {
@@ -324,6 +324,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStr
     const int items0 = p.B * p.ntypes * p.H * nblk, items1 = p.B * nblk * nblk;
     attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, attn_threads(0), kASmem, st>>>(tmQ, tmP, p);
     if (int e = check_launch("attn_tc_kernel<stats>")) return e;
+    if (stats_only) return 0;
     attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, attn_threads(1), kASmem, st>>>(tmQ, tmP, p);
     return check_launch("attn_tc_kernel<probs>");
 }

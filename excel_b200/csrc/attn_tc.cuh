@@ -21,6 +21,21 @@ struct AttnParams {
     int write_p;            // also emit the split-fp16 P operand [B*H*N, 2*np] (scaled by 2^10) for the P V GEMM (ntypes == 1)
 };
 
-int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st);
+// stats pass (always) + probs pass (head-reduced map, optionally the P operand); stats_only skips the second
+int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st, bool stats_only = false);
+
+// Fused probabilities + head-reduced map + P V for one score set (attn_pv.cu); needs the stats pass's `ml`.
+struct AttnPvParams {
+    int B, H, N, np, D;     // D = 64 H
+    int xo, yo;             // column offsets of X (queries) / Y (keys) in the split qkv matrix
+    int lo_off;
+    float alpha;            // scale * log2(e)
+    const float* ml;        // [B,H,N]  m + log2(l) - 10
+    float* out;             // [B,N,N] = coef * sum_h P[b,h]
+    float coef;
+    __half* o;              // split-fp16 [B*N, 2*D] (hi | lo): O[b, :, h*64..] = P[b,h] V[b,h]
+};
+// tmQ: split qkv [B*N, 6D], box 64 x 128 rows; tmV: split V^T [B*D, 2*np], box 64 keys x 64 rows
+int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st);
 
 }  // namespace xl

@@ -10,6 +10,7 @@
 // surgery blocks update feats[l-1] / feats[first-1] in place exactly where the reference's in-place `+=`
 // mutates the views it had already appended.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "excel_b200.h"
@@ -207,7 +208,7 @@ static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float 
     return attn_scores(c.m.qkv_a, p, write_p ? c.w.P : nullptr, c.st);
 }
 
-// o_s[b, :, h*dh..] = P[b,h] V[b,h]   (split output feeding the out projection)
+// o_s[b, :, h*dh..] = P[b,h] V[b,h] from a materialised P (debug path: EXCEL_ATTN_UNFUSED)
 static int attn_v(const Ctx& c) {
     TcParams p = {};
     p.M = c.N; p.N = c.dh; p.kblocks = c.np / 64; p.a_lo_off = c.np; p.b_lo_off = c.np; p.nb2 = c.H;
@@ -216,6 +217,23 @@ static int attn_v(const Ctx& c) {
     p.alpha = 1.f / kProbScale;
     p.Cs = c.w.o; p.lds = 2 * c.D; p.cs1 = (int64_t)c.N * 2 * c.D; p.cs2 = c.dh; p.cs_lo_off = c.D;
     return tc_gemm(c.m.P, c.m.vt64, p, c.B * c.H, 64, c.st);
+}
+
+// Original-path attention in one fused kernel after the stats pass (attn_pv.cu): out = coef * sum_h softmax(q_h k_h^T),
+// o_s[b, :, h*dh..] = softmax(q_h k_h^T) V[b,h] -- the per-head probabilities stay in tensor memory.
+static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
+    static const bool unfused = getenv("EXCEL_ATTN_UNFUSED") != nullptr;   // debug: materialise P, separate P V GEMM
+    AttnParams p = {};
+    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.ntypes = 1; p.lo_off = 3 * c.D;
+    p.xo[0] = 0; p.yo[0] = c.D;
+    p.alpha = scale * 1.4426950408889634f;  // exp2 domain
+    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.write_p = unfused;
+    if (int e = attn_scores(c.m.qkv_a, p, unfused ? c.w.P : nullptr, c.st, !unfused)) return e;
+    if (unfused) return attn_v(c);
+    AttnPvParams q = {};
+    q.B = c.B; q.H = c.H; q.N = c.N; q.np = c.np; q.D = c.D; q.xo = 0; q.yo = c.D; q.lo_off = 3 * c.D;
+    q.alpha = p.alpha; q.ml = c.w.m; q.out = out; q.coef = coef; q.o = c.w.o;
+    return attn_pv(c.m.qkv_a, c.m.vt64, q, c.st);
 }
 
 // ln_1 -> in_proj -> split qkv, V^T
@@ -330,7 +348,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         if (int e = check_launch("layernorm_kernel<embed>")) return e;
     }
 
-    const int qk_x[1] = {0}, qk_y[1] = {D}, self_xy[3] = {0, D, 2 * D};  // column blocks of qkv: q, k, v
+    const int self_xy[3] = {0, D, 2 * D};  // column blocks of qkv: q, k, v
     const float* x = c.w.x0;  // current single-path state (blocks before the surgery)
     for (int l = 0; l < L; ++l) {
         const ExcelVitLayer& Lw = Wt->blocks[l];
@@ -348,8 +366,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
             if (int e = qkv_stage(c, x, Lw, m_in)) return e;
-            if (int e = scores(c, 1, qk_x, qk_y, scale, attn_l, 1.f / H, 1)) return e;  // need_weights: head mean
-            if (int e = attn_v(c)) return e;
+            if (int e = attention_qk(c, scale, attn_l, 1.f / H)) return e;    // need_weights: head mean; o = attn @ v
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
             x = feat_l;
@@ -368,8 +385,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                 if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
-            if (int e = scores(c, 1, qk_x, qk_y, scale, attn_l, 1.f, 1)) return e;
-            if (int e = attn_v(c)) return e;                                  // x_ori = attn_ori @ v
+            if (int e = attention_qk(c, scale, attn_l, 1.f)) return e;          // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
             float* mid = (l == first) ? c.w.mid : src;
