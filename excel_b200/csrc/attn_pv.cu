@@ -33,8 +33,9 @@ constexpr uint32_t kXYStage = 4 * kTile;        // X_hi, X_lo, Y_hi, Y_lo
 constexpr uint32_t kVBox = 64 * 64 * 2;         // 8 KB: 64 head-dim rows x 64 keys of V^T
 constexpr uint32_t kVStage = 4 * kVBox;         // hi keys 0..63, hi keys 64..127, lo keys 0..63, lo keys 64..127
 constexpr int kXYStages = 2, kVStages = 2;
-constexpr uint32_t kStg = 2 * 16384;            // head-sum staging, one 128 x 32 fp32 block per epilogue team
-constexpr int kPvThreads = 64 + 256;
+constexpr uint32_t kStg = 16 * 2048;             // head-sum staging: one 32 x 16 fp32 block per epilogue warp
+constexpr int kPvEpiWarps = 16;              // four per TMEM lane group, 32 columns of every S tile each
+constexpr int kPvThreads = 64 + 32 * kPvEpiWarps;
 constexpr size_t kPvSmem = kXYStages * kXYStage + kVStages * kVStage + kStg + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float ex2a(float x) {
@@ -46,7 +47,8 @@ __device__ __forceinline__ float ex2a(float x) {
 }  // namespace
 
 __global__ void __launch_bounds__(kPvThreads, 1)
-attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV, const AttnPvParams p) {
+attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+               const __grid_constant__ CUtensorMap tmO, const AttnPvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* xy = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* vs = xy + kXYStages * kXYStage;
@@ -55,9 +57,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* xy_empty = xy_full + kXYStages;
     uint64_t* v_full = xy_empty + kXYStages;
     uint64_t* v_empty = v_full + kVStages;
-    uint64_t* s_full = v_empty + kVStages;    // [2] S tile complete (MMA -> epilogue)
-    uint64_t* p_ready = s_full + 2;           // [2] P written back into the S tile (epilogue -> MMA)
-    uint64_t* o_full = p_ready + 2;           // O of the head group complete (MMA -> epilogue)
+    uint64_t* s_full = v_empty + kVStages;    // [4] S sub-tile complete (MMA -> epilogue)
+    uint64_t* p_ready = s_full + 4;           // [4] P written back into the S sub-tile (epilogue -> MMA)
+    uint64_t* o_full = p_ready + 4;           // O of the head group complete (MMA -> epilogue)
     uint64_t* o_empty = o_full + 1;           // O drained (epilogue -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
@@ -69,9 +71,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXYStages; ++s) { mbar_init(&xy_full[s], 1); mbar_init(&xy_empty[s], 1); }
         for (int s = 0; s < kVStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], 8); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], kPvEpiWarps); }
         mbar_init(o_full, 1);
-        mbar_init(o_empty, 8);
+        mbar_init(o_empty, kPvEpiWarps);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -80,236 +82,282 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 256;
+    constexpr uint32_t kIdescPV = make_idesc(64);
+
+    // A "load step" is one (key block kb, head hh) pair: one X / Y stage and one V^T stage.  It is consumed as one or two
+    // 64-key SUB-STEPS (the last key block of an image may hold <= 64 valid keys), each with its own 64-column S / P buffer:
+    // four buffers in flight hide the MMA -> epilogue -> MMA round trip that a 128-key double buffer exposes.
+    const int last_valid = p.N - (nblk - 1) * 128;          // valid keys of the last key block (1..128)
+    const int nsub_last = last_valid > 64 ? 2 : 1;
 
     if (warp == 0) {
-        // ---- TMA producer: per step (key block kb, head h) the X / Y tiles, then that step's V^T tiles
-        if (lane == 0) {
-            tma_prefetch_desc(&tmQ);
-            tma_prefetch_desc(&tmV);
-            uint32_t n = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int rb = item % nblk, b = item / nblk;
-                for (int g = 0; g < ngrp; ++g) {
-                    const int hc = min(kHG, p.H - g * kHG);
-                    for (int kb = 0; kb < nblk; ++kb)
-                        for (int hh = 0; hh < hc; ++hh, ++n) {
-                            const int h = g * kHG + hh;
-                            const int s = n % kXYStages, ph = (n / kXYStages) & 1;
-                            mbar_wait(&xy_empty[s], ph ^ 1);
-                            uint8_t* st = xy + s * kXYStage;
+        // ---- TMA producer: the X / Y ring and the V^T ring advance independently (each polled without blocking), so a
+        // V^T stage waiting for its P V MMAs never holds back the X / Y tiles of later steps.
+        {
+            const bool leader = elect_one_sync();
+            if (leader) {
+                tma_prefetch_desc(&tmQ);
+                tma_prefetch_desc(&tmV);
+            }
+            struct It { int item, g, kb, hh; };
+            auto advance = [&](It& it) {
+                const int hc = min(kHG, p.H - it.g * kHG);
+                if (++it.hh < hc) return;
+                it.hh = 0;
+                if (++it.kb < nblk) return;
+                it.kb = 0;
+                if (++it.g < ngrp) return;
+                it.g = 0;
+                it.item += gridDim.x;
+            };
+            It ix = {(int)blockIdx.x, 0, 0, 0}, iv = ix;
+            uint32_t nx = 0, nv = 0;
+            while (ix.item < items || iv.item < items) {
+                if (ix.item < items) {
+                    const int s = nx % kXYStages;
+                    if (mbar_try(&xy_empty[s], ((nx / kXYStages) & 1) ^ 1)) {
+                        const int rb = ix.item % nblk, b = ix.item / nblk, h = ix.g * kHG + ix.hh;
+                        uint8_t* st = xy + s * kXYStage;
+                        const int xr = b * p.N + rb * 128, yr = b * p.N + ix.kb * 128;
+                        const int xc = p.xo + h * 64, yc = p.yo + h * 64;
+                        if (leader) {
                             mbar_arrive_expect_tx(&xy_full[s], kXYStage);
-                            const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
-                            const int xc = p.xo + h * 64, yc = p.yo + h * 64;
                             tma_load_2d(st, &tmQ, &xy_full[s], xc, xr);
                             tma_load_2d(st + kTile, &tmQ, &xy_full[s], xc + p.lo_off, xr);
                             tma_load_2d(st + 2 * kTile, &tmQ, &xy_full[s], yc, yr);
                             tma_load_2d(st + 3 * kTile, &tmQ, &xy_full[s], yc + p.lo_off, yr);
-                            const int sv = n % kVStages, pv = (n / kVStages) & 1;
-                            mbar_wait(&v_empty[sv], pv ^ 1);
-                            uint8_t* vt = vs + sv * kVStage;
+                        }
+                        ++nx;
+                        advance(ix);
+                    }
+                }
+                if (iv.item < items) {
+                    const int sv = nv % kVStages;
+                    if (mbar_try(&v_empty[sv], ((nv / kVStages) & 1) ^ 1)) {
+                        const int b = iv.item / nblk, h = iv.g * kHG + iv.hh;
+                        uint8_t* vt = vs + sv * kVStage;
+                        const int vr = b * p.D + h * 64, k0 = iv.kb * 128;   // V^T rows = head-dim channels, columns = keys
+                        if (leader) {
                             mbar_arrive_expect_tx(&v_full[sv], kVStage);
-                            const int vr = b * p.D + h * 64, k0 = kb * 128;   // V^T rows = head-dim channels, columns = keys
                             tma_load_2d(vt, &tmV, &v_full[sv], k0, vr);
                             tma_load_2d(vt + kVBox, &tmV, &v_full[sv], k0 + 64, vr);
                             tma_load_2d(vt + 2 * kVBox, &tmV, &v_full[sv], p.np + k0, vr);
                             tma_load_2d(vt + 3 * kVBox, &tmV, &v_full[sv], p.np + k0 + 64, vr);
                         }
+                        ++nv;
+                        advance(iv);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer.  Issue order S(0), S(1), PV(0), S(2), PV(1), ...: tcgen05.mma executes in issue order, so S(j+2)
-        // may overwrite the buffer PV(j) reads its P from without a further barrier.
-        if (lane == 0) {
-            constexpr uint32_t kIdescPV = make_idesc(64);
-            uint32_t ns = 0, npv = 0, ngd = 0;
-            auto issue_s = [&](int kb) {
-                const int s = ns % kXYStages, buf = ns & 1;
-                mbar_wait(&xy_full[s], (ns / kXYStages) & 1);
-                tc_fence_after();
-                const int nvalid = min(128, p.N - kb * 128);
-                const uint32_t idesc = make_idesc((nvalid + 15) & ~15);
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * 128);
-                const uint32_t st = smem_u32(xy + s * kXYStage);
-                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTile);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTile), b_lo = umma_desc_sw128(st + 3 * kTile);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);
-                    umma_f16(tacc, a_hi + adv, b_lo + adv, idesc, k != 0);
-                    umma_f16(tacc, a_lo + adv, b_hi + adv, idesc, 1);
-                    umma_f16(tacc, a_hi + adv, b_hi + adv, idesc, 1);
-                }
-                umma_commit(&xy_empty[s]);
-                umma_commit(&s_full[buf]);
-                ++ns;
-            };
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                for (int g = 0; g < ngrp; ++g) {
-                    const int hc = min(kHG, p.H - g * kHG);
-                    const int steps = nblk * hc;
-                    issue_s(0);
-                    for (int j = 0; j < steps; ++j) {
-                        if (j + 1 < steps) issue_s((j + 1) / hc);
-                        const int kb = j / hc, hh = j - kb * hc;
-                        const int buf = npv & 1, sv = npv % kVStages;
-                        mbar_wait(&p_ready[buf], (npv >> 1) & 1);
-                        mbar_wait(&v_full[sv], (npv / kVStages) & 1);
-                        if (j == 0) mbar_wait(o_empty, (ngd & 1) ^ 1);   // the previous group's O has been read out
-                        tc_fence_after();
-                        const int nvalid = min(128, p.N - kb * 128);
-                        const int ksteps = (nvalid + 15) >> 4;
-                        const uint32_t pbase = tmem_base + (uint32_t)(buf * 128);
-                        const uint32_t vst = smem_u32(vs + sv * kVStage);
-                        const uint32_t d = tmem_o + (uint32_t)(hh * 64);
-                        for (int k = 0; k < ksteps; ++k) {
-                            // keys 16k..16k+15: chunk k/2 of the S tile holds hi at columns +0..15, lo at +16..31 (8 columns per k step)
-                            const uint32_t a_hi = pbase + (uint32_t)((k >> 1) * 32 + (k & 1) * 8), a_lo = a_hi + 16;
-                            const uint32_t box = vst + (uint32_t)((k >> 2) * kVBox) + (uint32_t)((k & 3) * 32);
-                            const uint64_t b_hi = umma_desc_sw128(box), b_lo = umma_desc_sw128(box + 2 * kVBox);
-                            umma_f16_ts(d, a_hi, b_lo, kIdescPV, (kb | k) != 0);
-                            umma_f16_ts(d, a_lo, b_hi, kIdescPV, 1);
-                            umma_f16_ts(d, a_hi, b_hi, kIdescPV, 1);
+        // ---- MMA issuer (whole warp runs the control flow, one elected lane issues).  Within a head group the S tiles run
+        // up to four sub-steps ahead of the P V products: S(0..3), PV(0), S(4), PV(1), S(5), ...  tcgen05.mma executes in
+        // issue order, so S(u+4) may overwrite the buffer PV(u) reads its P from without a further barrier.
+        const bool leader = elect_one_sync();
+        struct Sub { int kb, hh, half; };             // position inside a head group
+        uint32_t gs = 0, gp = 0;          // sub-steps issued (S / PV), across items: buffer = count & 3
+        uint32_t ls = 0, lp = 0;          // load steps consumed (S / PV): ring stages and phases
+        uint32_t ngd = 0;
+        const uint32_t xy0 = smem_u32(xy), vs0 = smem_u32(vs);
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            for (int g = 0; g < ngrp; ++g) {
+                const int hc = min(kHG, p.H - g * kHG);
+                const int U = ((nblk - 1) * 2 + nsub_last) * hc;
+                auto next = [&](Sub& q) {     // sub-step order: key block, head, 64-key half
+                    const int nsub = q.kb < nblk - 1 ? 2 : nsub_last;
+                    if (++q.half < nsub) return;
+                    q.half = 0;
+                    if (++q.hh < hc) return;
+                    q.hh = 0;
+                    ++q.kb;
+                };
+                Sub qs = {0, 0, 0}, qp = {0, 0, 0};
+                int us = 0;
+                for (int up = 0; up < U; ++up) {
+                    for (; us < U && us < up + 4; ++us, ++gs) {   // ---- S(us) = X Y[64-key half]^T
+                        const int nsub = qs.kb < nblk - 1 ? 2 : nsub_last;
+                        const uint32_t s = ls % kXYStages;
+                        if (qs.half == 0) {
+                            mbar_wait(&xy_full[s], (ls / kXYStages) & 1);
+                            tc_fence_after();
                         }
-                        umma_commit(&v_empty[sv]);
-                        ++npv;
+                        const int nvalid = min(64, p.N - qs.kb * 128 - qs.half * 64);
+                        const uint32_t idesc = make_idesc((nvalid + 15) & ~15);
+                        const uint32_t tacc = tmem_base + (gs & 3) * 64;
+                        const uint32_t st = xy0 + s * kXYStage, yb = st + 2 * kTile + (uint32_t)qs.half * 8192u;   // Y rows 64..127: +64 x 128 B
+                        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTile);
+                        const uint64_t b_hi = umma_desc_sw128(yb), b_lo = umma_desc_sw128(yb + kTile);
+                        if (leader) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_f16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, k != 0);
+                                umma_f16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
+                                umma_f16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                            }
+                            if (qs.half == nsub - 1) umma_commit(&xy_empty[s]);
+                            umma_commit(&s_full[gs & 3]);
+                        }
+                        if (qs.half == nsub - 1) ++ls;
+                        next(qs);
                     }
-                    umma_commit(o_full);
-                    ++ngd;
+                    // ---- PV(up): O_hh += P[64 keys] V_hh
+                    const int nsub = qp.kb < nblk - 1 ? 2 : nsub_last;
+                    const uint32_t buf = gp & 3, sv = lp % kVStages;
+                    mbar_wait(&p_ready[buf], (gp >> 2) & 1);
+                    if (qp.half == 0) mbar_wait(&v_full[sv], (lp / kVStages) & 1);
+                    if (up == 0) mbar_wait(o_empty, (ngd & 1) ^ 1);   // the previous group's O has been read out
+                    tc_fence_after();
+                    const int nvalid = min(64, p.N - qp.kb * 128 - qp.half * 64);
+                    const uint32_t pbase = tmem_base + buf * 64;
+                    const uint32_t vbox = vs0 + sv * kVStage + (uint32_t)qp.half * kVBox;
+                    const uint64_t b_hi = umma_desc_sw128(vbox), b_lo = umma_desc_sw128(vbox + 2 * kVBox);
+                    const uint32_t d = tmem_o + (uint32_t)(qp.hh * 64);
+                    const uint32_t first = (qp.kb | qp.half) != 0;
+                    if (leader && !(p.dbg & 1)) {
+                        // keys 16k..16k+15 of the sub-tile live in its columns 16k..16k+15: hi pairs in +0..7, lo pairs in +8..15
+                        if (nvalid > 48) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_f16_ts(d, pbase + 16 * k, b_lo + 2 * k, kIdescPV, k ? 1u : first);
+                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 2 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_hi + 2 * k, kIdescPV, 1);
+                            }
+                        } else {
+                            for (int k = 0; k < ((nvalid + 15) >> 4); ++k) {
+                                umma_f16_ts(d, pbase + 16 * k, b_lo + 2 * k, kIdescPV, k ? 1u : first);
+                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 2 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_hi + 2 * k, kIdescPV, 1);
+                            }
+                        }
+                    }
+                    if (leader && qp.half == nsub - 1) umma_commit(&v_empty[sv]);
+                    if (qp.half == nsub - 1) ++lp;
+                    ++gp;
+                    next(qp);
                 }
+                if (leader) umma_commit(o_full);
+                ++ngd;
             }
         }
     } else {
-        // ---- epilogue warps: warp (lg, half) owns TMEM lanes 32*lg..+31 (query rows) and columns 64*half..+63 of every S tile
-        const int ew = warp - 2, lg = warp & 3, half = ew >> 2;
+        // ---- epilogue warps: warp (lg, qt) owns TMEM lanes 32*lg..+31 (query rows) and columns 16*qt..+15 of every 64-key
+        // sub-tile: S -> registers -> p -> split fp16 written back over the same 16 columns (hi pairs in +0..7, lo pairs
+        // in +8..15), so a warp only ever overwrites scores it has already read.
+        const int ew = warp - 2, lg = warp & 3, qt = ew >> 2;
         const int trow = lg * 32 + lane;
-        const int team_bar = 1 + half;
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
-        float* stg = reinterpret_cast<float*>(stg_base + half * 16384);
-        const int tid = (ew & 3) * 32 + lane, sub = tid >> 3, c4 = (tid & 7) * 4;
-        uint32_t ns = 0, ngd = 0;
+        float* stg = reinterpret_cast<float*>(stg_base) + ew * 512;   // warp-private 32 rows x 16 floats
+        uint32_t gu = 0, ngd = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int rb = item % nblk, b = item / nblk;
             const int row = rb * 128 + trow;
             const bool row_ok = row < p.N;
+            const int nrow = min(32, p.N - rb * 128 - lg * 32);       // valid rows of this warp's 32 (may be <= 0)
             for (int g = 0; g < ngrp; ++g) {
                 const int hc = min(kHG, p.H - g * kHG);
                 const float* mrow = p.ml + ((int64_t)b * p.H + g * kHG) * p.N + row;   // + hh * N
                 for (int kb = 0; kb < nblk; ++kb) {
-                    float acc[2][32];
+                    const int nsub = kb < nblk - 1 ? 2 : nsub_last;
+                    float acc[2][16];
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc)
+                    for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) acc[cc][e] = 0.f;
+                        for (int e = 0; e < 16; ++e) acc[hf][e] = 0.f;
                     float m_next = row_ok ? __ldg(mrow) : INFINITY;   // rows past N: exp2(-inf) = 0
-                    for (int hh = 0; hh < hc; ++hh, ++ns) {
+                    for (int hh = 0; hh < hc; ++hh) {
                         const float m_row = m_next;
                         if (row_ok && hh + 1 < hc) m_next = __ldg(mrow + (int64_t)(hh + 1) * p.N);
-                        const int buf = ns & 1;
-                        mbar_wait(&s_full[buf], (ns >> 1) & 1);
-                        tc_fence_after();
 #pragma unroll
-                        for (int cc = 0; cc < 2; ++cc) {
-                            const int c = half * 2 + cc;
-                            const int key0 = kb * 128 + c * 32;
-                            if (key0 >= p.N) continue;   // (uniform) chunk of padding keys: neither S nor P columns are used
-                            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 128 + c * 32);
-                            uint32_t r[32];
-                            tmem_ld32(taddr, r);
-                            if (key0 + 32 > p.N) {
+                        for (int hf = 0; hf < 2; ++hf) {
+                            if (hf >= nsub) break;
+                            const int buf = gu & 3;
+                            mbar_wait(&s_full[buf], (gu >> 2) & 1);
+                            tc_fence_after();
+                            const int key0 = kb * 128 + hf * 64 + qt * 16;
+                            if (key0 < p.N && !(p.dbg & 2)) {     // (uniform) else: padding keys only, neither the S nor the P columns are used
+                                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + qt * 16);
+                                uint32_t r[16];
+                                tmem_ld16(taddr, r);
+                                if (key0 + 16 > p.N) {
 #pragma unroll
-                                for (int e = 0; e < 32; ++e)
-                                    if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
+                                    for (int e = 0; e < 16; ++e)
+                                        if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
+                                }
+                                uint32_t ph[8], pl[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
+                                    const float v0 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e]), -m_row));
+                                    const float v1 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e + 1]), -m_row));
+                                    acc[hf][2 * e] += v0;
+                                    acc[hf][2 * e + 1] += v1;
+                                    const __half2 hh2 = __floats2half2_rn(v0, v1);
+                                    const float2 hf2 = __half22float2(hh2);
+                                    const __half2 ll2 = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
+                                    ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
+                                    pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
+                                }
+                                tmem_st8(taddr, ph);       // P_hi: keys (2e, 2e+1) of the chunk in column e
+                                tmem_st8(taddr + 8, pl);   // P_lo
+                                tmem_st_wait();
                             }
-                            uint32_t ph[16], pl[16];
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) {
-                                // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
-                                const float v0 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e]), -m_row));
-                                const float v1 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e + 1]), -m_row));
-                                acc[cc][2 * e] += v0;
-                                acc[cc][2 * e + 1] += v1;
-                                const __half2 hh2 = __floats2half2_rn(v0, v1);
-                                const float2 hf = __half22float2(hh2);
-                                const __half2 ll2 = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-                                ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
-                                pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
-                            }
-                            tmem_st16(taddr, ph);        // P_hi: keys (2e, 2e+1) of the chunk in column e
-                            tmem_st16(taddr + 16, pl);   // P_lo
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&p_ready[buf]);
+                            ++gu;
                         }
-                        tmem_st_wait();
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&p_ready[buf]);
                     }
-                    // head-reduced map of this key block: out[b,row,key] (+)= coef * 2^-10 * sum over the group's heads.
-                    // Staged per 32-column chunk in the team's buffer, written with 8 lanes per 128 B row segment.
-                    const float cf = p.coef * (1.f / 1024.f);
+                    // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
+                    // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
+                    // a reduce-add (performed in L2) for the others -- no thread waits on global memory.
+                    if (nrow > 0 && !(p.dbg & 4)) {
+                        const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
-                    for (int cc = 0; cc < 2; ++cc) {
-                        const int key0 = kb * 128 + (half * 2 + cc) * 32;
-                        if (key0 >= p.N) continue;  // (uniform)
-                        bar_sync(team_bar, 128);    // the previous chunk has been read out of the staging buffer
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int kc = kb * 128 + hf * 64 + qt * 16;
+                            if (kc >= p.N) break;   // (uniform)
+                            if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
+                            __syncwarp();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)   // row-rotated columns: conflict-free without padding
-                            stg[trow * 32 + ((e + trow) & 31)] = cf * acc[cc][e];
-                        bar_sync(team_bar, 128);
-                        const int nrow = min(128, p.N - rb * 128);
-                        if (g == 0) {
-                            for (int rr = sub; rr < nrow; rr += 16) {
-                                float* o = p.out + ((int64_t)b * p.N + rb * 128 + rr) * p.N + key0 + c4;
-#pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (key0 + c4 + e < p.N) o[e] = stg[rr * 32 + ((c4 + e + rr) & 31)];
-                            }
-                        } else {
-                            for (int r0 = sub; r0 < nrow; r0 += 64) {   // 4 rows per thread in flight: batches the L2 round trips
-                                float old[4][4];
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int rr = r0 + 16 * q;
-                                    const float* o = p.out + ((int64_t)b * p.N + rb * 128 + rr) * p.N + key0 + c4;
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) old[q][e] = (rr < nrow && key0 + c4 + e < p.N) ? o[e] : 0.f;
-                                }
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int rr = r0 + 16 * q;
-                                    if (rr >= nrow) break;
-                                    float* o = p.out + ((int64_t)b * p.N + rb * 128 + rr) * p.N + key0 + c4;
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e)
-                                        if (key0 + c4 + e < p.N) o[e] = old[q][e] + stg[rr * 32 + ((c4 + e + rr) & 31)];
-                                }
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                                    make_float4(cf * acc[hf][4 * j], cf * acc[hf][4 * j + 1], cf * acc[hf][4 * j + 2], cf * acc[hf][4 * j + 3]);
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (g == 0) tma_store_3d(&tmO, stg, kc, rb * 128 + lg * 32, b);
+                                else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, b);
+                                tma_store_commit();
                             }
                         }
                     }
                 }
-                // ---- O of the group's heads: TMEM -> split fp16 -> o[b*N + row, h*64 ..] (hi) / [.. + D] (lo)
+                if (lane == 0) tma_store_wait_all<0>();   // this group's map blocks are performed before the next group adds to them
+                // ---- O of head hh = qt of the group: TMEM -> split fp16 -> o[b*N + row, h*64 ..] (hi) / [.. + D] (lo)
                 mbar_wait(o_full, ngd & 1);
                 tc_fence_after();
+                if (qt < hc) {
 #pragma unroll 1
-                for (int q = 0; q < 4; ++q) {      // this warp's 128 columns = heads 2*half, 2*half+1 (two 32-column chunks each)
-                    const int hh = half * 2 + (q >> 1);
-                    if (hh >= hc) break;
-                    uint32_t r[32];
-                    tmem_ld32(tmem_o + lane_addr + (uint32_t)(half * 128 + q * 32), r);
-                    if (row_ok) {
-                        __half* oh = p.o + ((int64_t)b * p.N + row) * (2 * p.D) + (g * kHG + hh) * 64 + (q & 1) * 32;
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t r[16];
+                        tmem_ld16(tmem_o + lane_addr + (uint32_t)(qt * 64 + q * 16), r);
+                        if (row_ok) {
+                            __half* oh = p.o + ((int64_t)b * p.N + row) * (2 * p.D) + (g * kHG + qt) * 64 + q * 16;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __align__(16) __half2 h2[4], l2[4];
+                            for (int j = 0; j < 2; ++j) {
+                                __align__(16) __half2 h2[4], l2[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float v0 = __uint_as_float(r[8 * j + 2 * e]) * (1.f / 1024.f);
-                                const float v1 = __uint_as_float(r[8 * j + 2 * e + 1]) * (1.f / 1024.f);
-                                h2[e] = __floats2half2_rn(v0, v1);
-                                const float2 hf = __half22float2(h2[e]);
-                                l2[e] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                                for (int e = 0; e < 4; ++e) {
+                                    const float v0 = __uint_as_float(r[8 * j + 2 * e]) * (1.f / 1024.f);
+                                    const float v1 = __uint_as_float(r[8 * j + 2 * e + 1]) * (1.f / 1024.f);
+                                    h2[e] = __floats2half2_rn(v0, v1);
+                                    const float2 hf2 = __half22float2(h2[e]);
+                                    l2[e] = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
+                                }
+                                *reinterpret_cast<uint4*>(oh + 8 * j) = *reinterpret_cast<const uint4*>(h2);
+                                *reinterpret_cast<uint4*>(oh + p.D + 8 * j) = *reinterpret_cast<const uint4*>(l2);
                             }
-                            *reinterpret_cast<uint4*>(oh + 8 * j) = *reinterpret_cast<const uint4*>(h2);
-                            *reinterpret_cast<uint4*>(oh + p.D + 8 * j) = *reinterpret_cast<const uint4*>(l2);
                         }
                     }
                 }
@@ -328,6 +376,21 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 }
 
+__global__ void attn_compact_kernel(const float* __restrict__ src, int Npad, float* __restrict__ dst, int N) {
+    const int64_t row = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x)
+        dst[row * N + c] = __ldg(src + row * Npad + c);
+}
+
+int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st) {
+    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        const int nr = (int)(rows - r0 < 65535 ? rows - r0 : 65535);
+        attn_compact_kernel<<<dim3(ceil_div(N, 512), nr), 512, 0, st>>>(padded + r0 * Npad, Npad, out + r0 * N, N);
+        if (int e = check_launch("attn_compact_kernel")) return e;
+    }
+    return 0;
+}
+
 int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -336,8 +399,17 @@ int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& 
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.D == p.H * 64, "attn_pv: bad shape");
     XL_REQUIRE(p.ml && p.out && p.o, "attn_pv: missing buffers");
+    const int Npad = (p.N + 3) & ~3;
+    CUtensorMap tmO;
+    {
+        const uint64_t dims[3] = {(uint64_t)Npad, (uint64_t)p.N, (uint64_t)p.B};
+        const uint64_t strides[2] = {(uint64_t)Npad * 4, (uint64_t)Npad * 4 * p.N};
+        const uint32_t box[3] = {16, 32, 1};
+        if (int e = encode_tensor_map(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
+            return e;
+    }
     const int items = p.B * ((p.N + 127) / 128);
-    attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmV, p);
+    attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmV, tmO, p);
     return check_launch("attn_pv_kernel");
 }
 

@@ -85,39 +85,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            tma_prefetch_desc(&tmQ);
-            int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x)
-                for (int j = 0; j < inner; ++j, ++it) {
-                    int b, h, rb, kb;
-                    decode(item, j, b, h, rb, kb);
-                    const int s = it % kAStages;
-                    mbar_wait(&empty_bar[s], ((it / kAStages) & 1) ^ 1);
-                    uint8_t* st = tiles + s * kAStage;
+        // whole warp runs the control flow, one elected lane issues (keeps the TMA / tcgen05 operands on the uniform datapath)
+        const bool leader = elect_one_sync();
+        if (leader) tma_prefetch_desc(&tmQ);
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x)
+            for (int j = 0; j < inner; ++j, ++it) {
+                int b, h, rb, kb;
+                decode(item, j, b, h, rb, kb);
+                const int s = it % kAStages;
+                mbar_wait(&empty_bar[s], ((it / kAStages) & 1) ^ 1);
+                uint8_t* st = tiles + s * kAStage;
+                const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
+                const int ty = h / p.H, hd = h - ty * p.H;
+                const int xc = p.xo[ty] + hd * kABK, yc = p.yo[ty] + hd * kABK;
+                if (leader) {
                     mbar_arrive_expect_tx(&full_bar[s], kAStage);
-                    const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
-                    const int ty = h / p.H, hd = h - ty * p.H;
-                    const int xc = p.xo[ty] + hd * kABK, yc = p.yo[ty] + hd * kABK;
                     tma_load_2d(st, &tmQ, &full_bar[s], xc, xr);
                     tma_load_2d(st + kATile, &tmQ, &full_bar[s], xc + p.lo_off, xr);
                     tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], yc, yr);
                     tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], yc + p.lo_off, yr);
                 }
-        }
+            }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x)
-                for (int j = 0; j < inner; ++j, ++it) {
-                    const int buf = it & 1, s = it % kAStages;
-                    mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
-                    mbar_wait(&full_bar[s], (it / kAStages) & 1);
-                    tc_fence_after();
-                    const uint32_t tacc = tmem_base + (uint32_t)(buf * 128);
-                    const uint32_t st = smem_u32(tiles + s * kAStage);
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kATile);
-                    const uint64_t b_hi = umma_desc_sw128(st + 2 * kATile), b_lo = umma_desc_sw128(st + 3 * kATile);
+        const bool leader = elect_one_sync();
+        const uint32_t tiles0 = smem_u32(tiles);
+        int it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x)
+            for (int j = 0; j < inner; ++j, ++it) {
+                const int buf = it & 1, s = it % kAStages;
+                mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+                mbar_wait(&full_bar[s], (it / kAStages) & 1);
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * 128);
+                const uint32_t st = tiles0 + s * kAStage;
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kATile);
+                const uint64_t b_hi = umma_desc_sw128(st + 2 * kATile), b_lo = umma_desc_sw128(st + 3 * kATile);
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < kABK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -128,7 +132,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     umma_commit(&empty_bar[s]);
                     umma_commit(&acc_full[buf]);
                 }
-        }
+            }
     } else {
         // ---- epilogue: warp (lg, half): TMEM lanes 32*lg..+31 (rows), columns 32*CPW*half..+32*CPW-1 of every S tile
         constexpr int NPART = attn_epi_warps(MODE) / 4, CPW = 4 / NPART;   // column parts; 32-column chunks per warp

@@ -31,11 +31,14 @@ struct AttnPvParams {
     int lo_off;
     float alpha;            // scale * log2(e)
     const float* ml;        // [B,H,N]  m + log2(l) - 10
-    float* out;             // [B,N,N] = coef * sum_h P[b,h]
+    float* out;             // [B,N,Npad] scratch, Npad = round_up(N,4): coef * sum_h P[b,h], written by TMA store / reduce-add
     float coef;
     __half* o;              // split-fp16 [B*N, 2*D] (hi | lo): O[b, :, h*64..] = P[b,h] V[b,h]
+    int dbg;                // timing experiments only (EXCEL_PV_DBG): 1 no PV MMAs, 2 no epilogue math, 4 no map flush
 };
 // tmQ: split qkv [B*N, 6D], box 64 x 128 rows; tmV: split V^T [B*D, 2*np], box 64 keys x 64 rows
 int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st);
+// dense [rows, N] <- padded [rows, Npad]
+int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st);
 
 }  // namespace xl

@@ -83,19 +83,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        // whole warp runs the control flow, one elected lane issues (keeps the TMA / tcgen05 operands on the uniform datapath)
+        const bool leader = elect_one_sync();
+        if (leader) {
             tma_prefetch_desc(&tmA);
             tma_prefetch_desc(&tmB);
-            int it = 0;  // running k-block counter across tiles
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                int m0, n0, z1, z2;
-                decode(t, m0, n0, z1, z2);
-                const int a_row = p.a_row0 + z1 * p.a_row1 + z2 * p.a_row2 + m0, a_col = p.a_col0 + z1 * p.a_col1 + z2 * p.a_col2;
-                const int b_row = p.b_row0 + z1 * p.b_row1 + z2 * p.b_row2 + n0, b_col = p.b_col0 + z1 * p.b_col1 + z2 * p.b_col2;
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const int s = it % kTcStages;
-                    mbar_wait(&empty_bar[s], ((it / kTcStages) & 1) ^ 1);
-                    uint8_t* st = tiles + s * kStageBytes;
+        }
+        int it = 0;  // running k-block counter across tiles
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m0, n0, z1, z2;
+            decode(t, m0, n0, z1, z2);
+            const int a_row = p.a_row0 + z1 * p.a_row1 + z2 * p.a_row2 + m0, a_col = p.a_col0 + z1 * p.a_col1 + z2 * p.a_col2;
+            const int b_row = p.b_row0 + z1 * p.b_row1 + z2 * p.b_row2 + n0, b_col = p.b_col0 + z1 * p.b_col1 + z2 * p.b_col2;
+            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                const int s = it % kTcStages;
+                mbar_wait(&empty_bar[s], ((it / kTcStages) & 1) ^ 1);
+                uint8_t* st = tiles + s * kStageBytes;
+                if (leader) {
                     mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
                     tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
                     tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
@@ -105,20 +109,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int it = 0, i = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
-                const int buf = i & 1;
-                mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        const bool leader = elect_one_sync();
+        const uint32_t tiles0 = smem_u32(tiles);
+        int it = 0, i = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
+            const int buf = i & 1;
+            mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(buf * kBN);
+            for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+                const int s = it % kTcStages;
+                mbar_wait(&full_bar[s], (it / kTcStages) & 1);
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * kBN);
-                for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-                    const int s = it % kTcStages;
-                    mbar_wait(&full_bar[s], (it / kTcStages) & 1);
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(tiles + s * kStageBytes);
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
-                    const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+                const uint32_t st = tiles0 + s * kStageBytes;
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
+                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 fp16 = 32 B further along K inside the swizzle atom
@@ -128,8 +134,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     umma_commit(&empty_bar[s]);  // stage s may be refilled once these MMAs have read it
                 }
-                umma_commit(&acc_full[buf]);     // accumulator complete
             }
+            if (leader) umma_commit(&acc_full[buf]);     // accumulator complete
         }
     } else {
         // ---- epilogue (warps 2..9).  Warp w owns TMEM lanes 32*(w%4)..+31 == tile rows 32*(w%4)+lane; the two teams

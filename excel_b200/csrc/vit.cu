@@ -147,7 +147,7 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 }
 
 struct Ws {  // workspace carve-up
-    float *pos, *m, *l, *pnew, *mid, *x0;
+    float *pos, *m, *l, *pnew, *pad, *mid, *x0;
     __half *col, *h, *qkv, *vt, *P, *pn, *o, *o2, *u;
 };
 
@@ -159,6 +159,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     t += align256((size_t)N * D * 4);                 // pos
     t += 2 * align256((size_t)3 * B * H * N * 4);     // softmax row stats m, l (up to 3 score sets)
     t += align256((size_t)B * N * N * 4);             // pnew
+    t += align256((size_t)B * N * ((N + 3) & ~3) * 4); // pad (row-padded attention map, TMA target)
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
     t += 3 * align256(BN * 2 * D * 2);                // h, o, o2
@@ -232,8 +233,11 @@ static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
     if (unfused) return attn_v(c);
     AttnPvParams q = {};
     q.B = c.B; q.H = c.H; q.N = c.N; q.np = c.np; q.D = c.D; q.xo = 0; q.yo = c.D; q.lo_off = 3 * c.D;
-    q.alpha = p.alpha; q.ml = c.w.m; q.out = out; q.coef = coef; q.o = c.w.o;
-    return attn_pv(c.m.qkv_a, c.m.vt64, q, c.st);
+    q.alpha = p.alpha; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
+    static const int dbg = getenv("EXCEL_PV_DBG") ? atoi(getenv("EXCEL_PV_DBG")) : 0;
+    q.dbg = dbg;
+    if (int e = attn_pv(c.m.qkv_a, c.m.vt64, q, c.st)) return e;
+    return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);
 }
 
 // ln_1 -> in_proj -> split qkv, V^T
@@ -297,6 +301,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         c.w.m = (float*)take((size_t)3 * B * H * N * 4);
         c.w.l = (float*)take((size_t)3 * B * H * N * 4);
         c.w.pnew = (float*)take((size_t)B * N * N * 4);
+        c.w.pad = (float*)take((size_t)B * N * ((N + 3) & ~3) * 4);
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
         c.w.col = (__half*)take((size_t)B * npatch * 2 * KKp * 2);
