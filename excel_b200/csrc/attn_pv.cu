@@ -399,15 +399,8 @@ int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& 
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.D == p.H * 64, "attn_pv: bad shape");
     XL_REQUIRE(p.ml && p.out && p.o, "attn_pv: missing buffers");
-    const int Npad = (p.N + 3) & ~3;
     CUtensorMap tmO;
-    {
-        const uint64_t dims[3] = {(uint64_t)Npad, (uint64_t)p.N, (uint64_t)p.B};
-        const uint64_t strides[2] = {(uint64_t)Npad * 4, (uint64_t)Npad * 4 * p.N};
-        const uint32_t box[3] = {16, 32, 1};
-        if (int e = encode_tensor_map(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B))
-            return e;
-    }
+    if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
     const int items = p.B * ((p.N + 127) / 128);
     attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmV, tmO, p);
     return check_launch("attn_pv_kernel");

@@ -10,19 +10,19 @@ namespace xl {
 // P[b,h] = softmax_j(alpha' * X_h Y_h^T), X/Y = column blocks (xo, yo; 64 columns per head) of the split-fp16
 // qkv matrix [B*N, 2*lo_off] (hi | lo).  alpha = scale * log2(e) (the kernels work in the exp2 domain).
 struct AttnParams {
-    int B, H, N, np;        // np = round_up(N, 64): key pitch of the P operand
+    int B, H, N;
     int ntypes;             // score sets summed into `out` by one launch (1, or 3 for the surgery new path: qq, kk, vv)
     int xo[3], yo[3];       // column offsets of X / Y per score set
     int lo_off;
     float alpha;
-    float *m, *l;           // [ntypes,B,H,N] row max (log2 domain) / row sum: written by the stats pass, read by the probs pass
-    float* out;             // [B,N,N] = coef * sum_types sum_h P[b,h]
+    float* m;               // [ntypes,B,H,N] row statistic m + log2(l) - 10: written by the stats pass, read by the map pass
+    float* out;             // row-padded map [B,N,Npad], Npad = round_up(N,4): coef * sum_types sum_h P[b,h]
     float coef;
-    int write_p;            // also emit the split-fp16 P operand [B*H*N, 2*np] (scaled by 2^10) for the P V GEMM (ntypes == 1)
 };
 
-// stats pass (always) + probs pass (head-reduced map, optionally the P operand); stats_only skips the second
-int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, __half* Ps, cudaStream_t st, bool stats_only = false);
+// stats pass (always) + map pass (skipped with stats_only)
+int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, cudaStream_t st, bool stats_only = false);
+int make_map_store(CUtensorMap* tm, float* base, int B, int N);
 
 // Fused probabilities + head-reduced map + P V for one score set (attn_pv.cu); needs the stats pass's `ml`.
 struct AttnPvParams {

@@ -147,8 +147,8 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 }
 
 struct Ws {  // workspace carve-up
-    float *pos, *m, *l, *pnew, *pad, *mid, *x0;
-    __half *col, *h, *qkv, *vt, *P, *pn, *o, *o2, *u;
+    float *pos, *m, *pnew, *pad, *mid, *x0;
+    __half *col, *h, *qkv, *vt, *pn, *o, *o2, *u;
 };
 
 static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
@@ -157,22 +157,20 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
     size_t t = 0;
     t += align256((size_t)N * D * 4);                 // pos
-    t += 2 * align256((size_t)3 * B * H * N * 4);     // softmax row stats m, l (up to 3 score sets)
-    t += align256((size_t)B * N * N * 4);             // pnew
-    t += align256((size_t)B * N * ((N + 3) & ~3) * 4); // pad (row-padded attention map, TMA target)
+    t += align256((size_t)3 * B * H * N * 4);         // softmax row statistic (up to 3 score sets)
+    t += 2 * align256((size_t)B * N * ((N + 3) & ~3) * 4); // pnew, pad (row-padded attention maps, TMA targets)
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
     t += 3 * align256(BN * 2 * D * 2);                // h, o, o2
     t += align256(BN * 6 * D * 2);                    // qkv
     t += align256((size_t)B * D * 2 * np * 2);        // vt
-    t += align256((size_t)B * H * N * 2 * np * 2);    // P
     t += align256(BN * 2 * np * 2);                   // pn
     t += align256(BN * 8 * D * 2);                    // u
     return t + 256;
 }
 
 struct Maps {  // tensor maps of the activation operands (built once per forward)
-    CUtensorMap col, h, qkv_a, qkv_b, vt64, vt128, P, pn, o, o2, u;
+    CUtensorMap col, h, qkv_a, qkv_b, vt64, vt128, pn, o, o2, u;
 };
 
 struct Ctx {
@@ -198,46 +196,30 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     return tc_gemm(ma, mw, p, 1, 128, c.st);
 }
 
-// out[b] = coef * sum over the score sets t and heads h of softmax(scale * X_t,h Y_t,h^T), X/Y column blocks (offsets
-// xo[t], yo[t]) of qkv_s, never materialising the scores (attn_tc.cu); write_p also emits the split P operand (1 set).
-static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float scale, float* out, float coef, int write_p) {
+// Row statistics of softmax(scale * X_t,h Y_t,h^T) for `ntypes` score sets (column blocks xo[t], yo[t] of qkv_s) and, unless
+// stats_only, the row-padded map  out[b] = coef * sum_t sum_h softmax(...)  -- the scores are never materialised (attn_tc.cu).
+static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float scale, float* out_padded, float coef,
+                  bool stats_only) {
     AttnParams p = {};
-    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.ntypes = ntypes; p.lo_off = 3 * c.D;
+    p.B = c.B; p.H = c.H; p.N = c.N; p.ntypes = ntypes; p.lo_off = 3 * c.D;
     for (int t = 0; t < ntypes; ++t) { p.xo[t] = xo[t]; p.yo[t] = yo[t]; }
     p.alpha = scale * 1.4426950408889634f;  // exp2 domain
-    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.write_p = write_p;
-    return attn_scores(c.m.qkv_a, p, write_p ? c.w.P : nullptr, c.st);
+    p.m = c.w.m; p.out = out_padded; p.coef = coef;
+    return attn_scores(c.m.qkv_a, p, c.st, stats_only);
 }
 
-// o_s[b, :, h*dh..] = P[b,h] V[b,h] from a materialised P (debug path: EXCEL_ATTN_UNFUSED)
-static int attn_v(const Ctx& c) {
-    TcParams p = {};
-    p.M = c.N; p.N = c.dh; p.kblocks = c.np / 64; p.a_lo_off = c.np; p.b_lo_off = c.np; p.nb2 = c.H;
-    p.a_row1 = c.H * c.N; p.a_row2 = c.N;
-    p.b_row1 = c.D; p.b_row2 = c.dh;
-    p.alpha = 1.f / kProbScale;
-    p.Cs = c.w.o; p.lds = 2 * c.D; p.cs1 = (int64_t)c.N * 2 * c.D; p.cs2 = c.dh; p.cs_lo_off = c.D;
-    return tc_gemm(c.m.P, c.m.vt64, p, c.B * c.H, 64, c.st);
-}
-
-// Original-path attention in one fused kernel after the stats pass (attn_pv.cu): out = coef * sum_h softmax(q_h k_h^T),
+// Original-path attention: stats pass, then ONE fused kernel (attn_pv.cu): out = coef * sum_h softmax(q_h k_h^T) and
 // o_s[b, :, h*dh..] = softmax(q_h k_h^T) V[b,h] -- the per-head probabilities stay in tensor memory.
 static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
-    static const bool unfused = getenv("EXCEL_ATTN_UNFUSED") != nullptr;   // debug: materialise P, separate P V GEMM
-    AttnParams p = {};
-    p.B = c.B; p.H = c.H; p.N = c.N; p.np = c.np; p.ntypes = 1; p.lo_off = 3 * c.D;
-    p.xo[0] = 0; p.yo[0] = c.D;
-    p.alpha = scale * 1.4426950408889634f;  // exp2 domain
-    p.m = c.w.m; p.l = c.w.l; p.out = out; p.coef = coef; p.write_p = unfused;
-    if (int e = attn_scores(c.m.qkv_a, p, unfused ? c.w.P : nullptr, c.st, !unfused)) return e;
-    if (unfused) return attn_v(c);
+    const int qx[1] = {0}, ky[1] = {c.D};
+    if (int e = scores(c, 1, qx, ky, scale, nullptr, 0.f, true)) return e;
     AttnPvParams q = {};
     q.B = c.B; q.H = c.H; q.N = c.N; q.np = c.np; q.D = c.D; q.xo = 0; q.yo = c.D; q.lo_off = 3 * c.D;
-    q.alpha = p.alpha; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
-    static const int dbg = getenv("EXCEL_PV_DBG") ? atoi(getenv("EXCEL_PV_DBG")) : 0;
+    q.alpha = scale * 1.4426950408889634f; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
+    static const int dbg = getenv("EXCEL_PV_DBG") ? atoi(getenv("EXCEL_PV_DBG")) : 0;   // timing experiments only
     q.dbg = dbg;
     if (int e = attn_pv(c.m.qkv_a, c.m.vt64, q, c.st)) return e;
-    return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);
+    return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);   // API layout [B,N,N]
 }
 
 // ln_1 -> in_proj -> split qkv, V^T
@@ -299,8 +281,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
         c.w.pos = (float*)take((size_t)N * D * 4);
         c.w.m = (float*)take((size_t)3 * B * H * N * 4);
-        c.w.l = (float*)take((size_t)3 * B * H * N * 4);
-        c.w.pnew = (float*)take((size_t)B * N * N * 4);
+        c.w.pnew = (float*)take((size_t)B * N * ((N + 3) & ~3) * 4);
         c.w.pad = (float*)take((size_t)B * N * ((N + 3) & ~3) * 4);
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
@@ -310,7 +291,6 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         c.w.o2 = (__half*)take(BN * 2 * D * 2);
         c.w.qkv = (__half*)take(BN * 6 * D * 2);
         c.w.vt = (__half*)take((size_t)B * D * 2 * np * 2);
-        c.w.P = (__half*)take((size_t)B * H * N * 2 * np * 2);
         c.w.pn = (__half*)take(BN * 2 * np * 2);
         c.w.u = (__half*)take(BN * 8 * D * 2);
     }
@@ -322,7 +302,6 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         e |= make_operand_map(&c.m.qkv_b, c.w.qkv, BN, 6 * D, 6 * D, 128);
         e |= make_operand_map(&c.m.vt64, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 64);
         e |= make_operand_map(&c.m.vt128, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 128);
-        e |= make_operand_map(&c.m.P, c.w.P, (int64_t)B * H * N, 2 * np, 2 * np, 128);
         e |= make_operand_map(&c.m.pn, c.w.pn, BN, 2 * np, 2 * np, 128);
         e |= make_operand_map(&c.m.o, c.w.o, BN, 2 * D, 2 * D, 128);
         e |= make_operand_map(&c.m.o2, c.w.o2, BN, 2 * D, 2 * D, 128);
@@ -380,8 +359,8 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
             if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
-            if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, 0)) return e;
-            if (int e = split_f16(c.w.pnew, N, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
+            if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, false)) return e;
+            if (int e = split_f16(c.w.pnew, (N + 3) & ~3, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
                 p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.b_lo_off = np; p.nb2 = 1;
