@@ -376,19 +376,28 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 }
 
-__global__ void attn_compact_kernel(const float* __restrict__ src, int Npad, float* __restrict__ dst, int N) {
-    const int64_t row = blockIdx.y;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x)
-        dst[row * N + c] = __ldg(src + row * Npad + c);
+// dense [rows, N] <- row-padded [rows, Npad]: one aligned 16 B load per thread, four coalesced scalar stores
+__global__ void __launch_bounds__(256)
+attn_compact_kernel(const float* __restrict__ src, int Npad, float* __restrict__ dst, int N, int64_t total4) {
+    const int n4 = Npad >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / n4;
+        const int c = (int)(i - row * n4) * 4;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + row * Npad + c));
+        float* o = dst + row * N + c;
+        o[0] = v.x;
+        if (c + 1 < N) o[1] = v.y;
+        if (c + 2 < N) o[2] = v.z;
+        if (c + 3 < N) o[3] = v.w;
+    }
 }
 
 int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st) {
-    for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
-        const int nr = (int)(rows - r0 < 65535 ? rows - r0 : 65535);
-        attn_compact_kernel<<<dim3(ceil_div(N, 512), nr), 512, 0, st>>>(padded + r0 * Npad, Npad, out + r0 * N, N);
-        if (int e = check_launch("attn_compact_kernel")) return e;
-    }
-    return 0;
+    XL_REQUIRE(Npad % 4 == 0 && Npad >= N && Npad - N < 4, "attn_compact: bad padding");
+    const int64_t total4 = rows * (Npad >> 2);
+    const int64_t blocks = ceil_div64(total4, 256 * 4);
+    attn_compact_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(padded, Npad, out, N, total4);
+    return check_launch("attn_compact_kernel");
 }
 
 int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st) {

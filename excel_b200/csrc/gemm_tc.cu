@@ -28,12 +28,17 @@
 
 namespace xl {
 
-constexpr int kBK = 64, kTcStages = 3;
+constexpr int kBK = 64;
 constexpr uint32_t kTileBytes = kBM * kBK * 2;        // one 128-row x 64-k fp16 tile: 16 KB
-constexpr uint32_t kStageBytes = 4 * kTileBytes;      // A_hi, A_lo, B_hi, B_lo (B tiles use BN*128 B of their slot)
 constexpr int kTcThreads = 64 + 256;                 // TMA producer warp, MMA warp, 8 epilogue warps
 constexpr uint32_t kEpiBytes = 2 * 16384;             // epilogue staging: two 128-row x 128 B blocks (TMA store sources)
-constexpr size_t kTcSmem = kTcStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+// Per tile width BN: a stage holds A_hi, A_lo (16 KB each) and B_hi, B_lo (BN x 128 B each).  An SM ingests ~64 B/clk from
+// L2, about what 128 x 128 tiles need to keep the tensor pipe busy (64 KB per 36 MMAs); 256-wide tiles move 96 KB per 72
+// MMAs and leave the pipe as the limit.  They take 2 x 256 TMEM columns and a 2-stage ring (2 x 96 KB).
+__host__ __device__ constexpr uint32_t tc_b_bytes(int bn) { return (uint32_t)bn * kBK * 2; }
+__host__ __device__ constexpr uint32_t tc_stage_bytes(int bn) { return 2 * kTileBytes + 2 * tc_b_bytes(bn); }
+__host__ __device__ constexpr int tc_stages(int bn) { return bn > 128 ? 2 : 3; }
+__host__ __device__ constexpr size_t tc_smem(int bn) { return tc_stages(bn) * tc_stage_bytes(bn) + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/; }
 
 // Persistent kernel: one CTA per SM walks the output tiles t = blockIdx.x + i*gridDim.x (n fastest, so
 // neighbouring CTAs share A rows in L2).  Two TMEM accumulators (2 x kBN columns) let the epilogue of tile i
@@ -48,6 +53,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int tiles_n, int tiles_m, int num_tiles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024 B alignment
+    constexpr int kTcStages = tc_stages(kBN);
+    constexpr uint32_t kStageBytes = tc_stage_bytes(kBN), kBBytes = tc_b_bytes(kBN);
     float* stage = reinterpret_cast<float*>(tiles + kTcStages * kStageBytes);      // epilogue staging, 128 x 36 floats
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + kTcStages * kStageBytes + kEpiBytes);
     uint64_t* empty_bar = full_bar + kTcStages;
@@ -103,8 +110,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
                     tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
                     tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
-                    tma_load_2d(st + 2 * kTileBytes, &tmB, &full_bar[s], b_col + kb * kBK, b_row);
-                    tma_load_2d(st + 3 * kTileBytes, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row);
+                    // B tiles wider than 128 rows arrive as stacked 128-row boxes (the operand maps keep a 128-row box)
+#pragma unroll
+                    for (int r = 0; r < kBN; r += 128) {
+                        tma_load_2d(st + 2 * kTileBytes + r * 128, &tmB, &full_bar[s], b_col + kb * kBK, b_row + r);
+                        tma_load_2d(st + 2 * kTileBytes + kBBytes + r * 128, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row + r);
+                    }
                 }
             }
         }
@@ -123,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t st = tiles0 + s * kStageBytes;
                 const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 3 * kTileBytes);
+                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 2 * kTileBytes + kBBytes);
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
@@ -333,15 +344,17 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(256)));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(256)));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(128)));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(128)));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(64)));
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(64)));
         attr_set = true;
     }
     XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1 && batch % p.nb2 == 0,
                "tc_gemm: bad shape M=%d N=%d kblocks=%d batch=%d", p.M, p.N, p.kblocks, batch);
-    XL_REQUIRE(bn == 64 || bn == 128, "tc_gemm: tile N must be 64 or 128 (the B tensor map's box must match)");
+    XL_REQUIRE(bn == 64 || bn == 128 || bn == 256, "tc_gemm: tile N must be 64, 128 or 256 (B tensor map box: 64 rows for 64, else 128)");
     XL_REQUIRE((p.C != nullptr) != (p.Cs != nullptr), "tc_gemm: exactly one of the fp32 / split-fp16 outputs");
     const int tiles_n = ceil_div(p.N, bn), tiles_m = ceil_div(p.M, kBM);
     const int64_t total = (int64_t)tiles_n * tiles_m * batch;
@@ -376,8 +389,9 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
             tma_epi = true;
         }
     }
-#define XL_TC_LAUNCH(BN_, EPI_) gemm_tc_kernel<BN_, EPI_><<<grid, kTcThreads, kTcSmem, st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
-    if (bn == 128) { if (tma_epi) XL_TC_LAUNCH(128, true); else XL_TC_LAUNCH(128, false); }
+#define XL_TC_LAUNCH(BN_, EPI_) gemm_tc_kernel<BN_, EPI_><<<grid, kTcThreads, tc_smem(BN_), st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
+    if (bn == 256) { if (tma_epi) XL_TC_LAUNCH(256, true); else XL_TC_LAUNCH(256, false); }
+    else if (bn == 128) { if (tma_epi) XL_TC_LAUNCH(128, true); else XL_TC_LAUNCH(128, false); }
     else { if (tma_epi) XL_TC_LAUNCH(64, true); else XL_TC_LAUNCH(64, false); }
 #undef XL_TC_LAUNCH
     return check_launch("gemm_tc_kernel");

@@ -193,7 +193,9 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     p.M = (int)c.BN; p.N = Nout; p.kblocks = K / 64; p.a_lo_off = K; p.b_lo_off = K; p.nb2 = 1;
     p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f; p.act = act;
     p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
-    return tc_gemm(ma, mw, p, 1, 128, c.st);
+    static const int force_bn = getenv("EXCEL_GEMM_BN") ? atoi(getenv("EXCEL_GEMM_BN")) : 0;   // tuning experiments only
+    const int bn = force_bn ? force_bn : (Nout % 256 == 0 ? 256 : 128);
+    return tc_gemm(ma, mw, p, 1, bn, c.st);
 }
 
 // Row statistics of softmax(scale * X_t,h Y_t,h^T) for `ntypes` score sets (column blocks xo[t], yo[t] of qkv_s) and, unless
