@@ -30,8 +30,7 @@ namespace {
 constexpr int kHG = 4;                          // heads per group (O accumulators: kHG x 64 TMEM columns)
 constexpr uint32_t kTile = 128 * 64 * 2;        // 16 KB: 128 rows x 64 halves (one SWIZZLE_128B operand tile)
 constexpr uint32_t kXYStage = 4 * kTile;        // X_hi, X_lo, Y_hi, Y_lo
-constexpr uint32_t kVBox = 64 * 64 * 2;         // 8 KB: 64 head-dim rows x 64 keys of V^T
-constexpr uint32_t kVStage = 4 * kVBox;         // hi keys 0..63, hi keys 64..127, lo keys 0..63, lo keys 64..127
+constexpr uint32_t kVStage = 2 * kTile;         // V_hi, V_lo: 128 keys x 64 head-dim channels, straight from the qkv matrix
 constexpr int kXYStages = 2, kVStages = 2;
 constexpr uint32_t kStg = 16 * 2048;             // head-sum staging: one 32 x 16 fp32 block per epilogue warp
 constexpr int kPvEpiWarps = 16;              // four per TMEM lane group, 32 columns of every S tile each
@@ -47,8 +46,7 @@ __device__ __forceinline__ float ex2a(float x) {
 }  // namespace
 
 __global__ void __launch_bounds__(kPvThreads, 1)
-attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
-               const __grid_constant__ CUtensorMap tmO, const AttnPvParams p) {
+attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmO, const AttnPvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* xy = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* vs = xy + kXYStages * kXYStage;
@@ -82,7 +80,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 256;
-    constexpr uint32_t kIdescPV = make_idesc(64);
+    constexpr uint32_t kIdescPV = make_idesc_bmn(64);   // B = V [keys, head dim]: MN-major
 
     // A "load step" is one (key block kb, head hh) pair: one X / Y stage and one V^T stage.  It is consumed as one or two
     // 64-key SUB-STEPS (the last key block of an image may hold <= 64 valid keys), each with its own 64-column S / P buffer:
@@ -97,7 +95,6 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const bool leader = elect_one_sync();
             if (leader) {
                 tma_prefetch_desc(&tmQ);
-                tma_prefetch_desc(&tmV);
             }
             struct It { int item, g, kb, hh; };
             auto advance = [&](It& it) {
@@ -136,13 +133,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if (mbar_try(&v_empty[sv], ((nv / kVStages) & 1) ^ 1)) {
                         const int b = iv.item / nblk, h = iv.g * kHG + iv.hh;
                         uint8_t* vt = vs + sv * kVStage;
-                        const int vr = b * p.D + h * 64, k0 = iv.kb * 128;   // V^T rows = head-dim channels, columns = keys
+                        const int vr = b * p.N + iv.kb * 128, vc = p.vo + h * 64;   // V rows = keys, columns = head-dim channels
                         if (leader) {
                             mbar_arrive_expect_tx(&v_full[sv], kVStage);
-                            tma_load_2d(vt, &tmV, &v_full[sv], k0, vr);
-                            tma_load_2d(vt + kVBox, &tmV, &v_full[sv], k0 + 64, vr);
-                            tma_load_2d(vt + 2 * kVBox, &tmV, &v_full[sv], p.np + k0, vr);
-                            tma_load_2d(vt + 3 * kVBox, &tmV, &v_full[sv], p.np + k0 + 64, vr);
+                            tma_load_2d(vt, &tmQ, &v_full[sv], vc, vr);
+                            tma_load_2d(vt + kTile, &tmQ, &v_full[sv], vc + p.lo_off, vr);
                         }
                         ++nv;
                         advance(iv);
@@ -210,8 +205,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tc_fence_after();
                     const int nvalid = min(64, p.N - qp.kb * 128 - qp.half * 64);
                     const uint32_t pbase = tmem_base + buf * 64;
-                    const uint32_t vbox = vs0 + sv * kVStage + (uint32_t)qp.half * kVBox;
-                    const uint64_t b_hi = umma_desc_sw128(vbox), b_lo = umma_desc_sw128(vbox + 2 * kVBox);
+                    const uint32_t vbox = vs0 + sv * kVStage + (uint32_t)qp.half * 8192u;   // keys 64..127: +64 rows x 128 B
+                    const uint64_t b_hi = umma_desc_sw128(vbox), b_lo = umma_desc_sw128(vbox + kTile);
                     const uint32_t d = tmem_o + (uint32_t)(qp.hh * 64);
                     const uint32_t first = (qp.kb | qp.half) != 0;
                     if (leader && !(p.dbg & 1)) {
@@ -219,15 +214,15 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         if (nvalid > 48) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_f16_ts(d, pbase + 16 * k, b_lo + 2 * k, kIdescPV, k ? 1u : first);
-                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 2 * k, kIdescPV, 1);
-                                umma_f16_ts(d, pbase + 16 * k, b_hi + 2 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_lo + 128 * k, kIdescPV, k ? 1u : first);
+                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 128 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_hi + 128 * k, kIdescPV, 1);
                             }
                         } else {
                             for (int k = 0; k < ((nvalid + 15) >> 4); ++k) {
-                                umma_f16_ts(d, pbase + 16 * k, b_lo + 2 * k, kIdescPV, k ? 1u : first);
-                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 2 * k, kIdescPV, 1);
-                                umma_f16_ts(d, pbase + 16 * k, b_hi + 2 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_lo + 128 * k, kIdescPV, k ? 1u : first);
+                                umma_f16_ts(d, pbase + 16 * k + 8, b_hi + 128 * k, kIdescPV, 1);
+                                umma_f16_ts(d, pbase + 16 * k, b_hi + 128 * k, kIdescPV, 1);
                             }
                         }
                     }
@@ -400,18 +395,18 @@ int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows,
     return check_launch("attn_compact_kernel");
 }
 
-int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st) {
+int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
         XL_CUDA(cudaFuncSetAttribute(attn_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPvSmem));
         attr_set = true;
     }
-    XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.np % 64 == 0 && p.np >= p.N && p.D == p.H * 64, "attn_pv: bad shape");
+    XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.D == p.H * 64, "attn_pv: bad shape");
     XL_REQUIRE(p.ml && p.out && p.o, "attn_pv: missing buffers");
     CUtensorMap tmO;
     if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
     const int items = p.B * ((p.N + 127) / 128);
-    attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmV, tmO, p);
+    attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmO, p);
     return check_launch("attn_pv_kernel");
 }
 

@@ -26,8 +26,8 @@ int make_map_store(CUtensorMap* tm, float* base, int B, int N);
 
 // Fused probabilities + head-reduced map + P V for one score set (attn_pv.cu); needs the stats pass's `ml`.
 struct AttnPvParams {
-    int B, H, N, np, D;     // D = 64 H
-    int xo, yo;             // column offsets of X (queries) / Y (keys) in the split qkv matrix
+    int B, H, N, D;         // D = 64 H
+    int xo, yo, vo;         // column offsets of X (queries) / Y (keys) / V (values) in the split qkv matrix
     int lo_off;
     float alpha;            // scale * log2(e)
     const float* ml;        // [B,H,N]  m + log2(l) - 10
@@ -36,8 +36,8 @@ struct AttnPvParams {
     __half* o;              // split-fp16 [B*N, 2*D] (hi | lo): O[b, :, h*64..] = P[b,h] V[b,h]
     int dbg;                // timing experiments only (EXCEL_PV_DBG): 1 no PV MMAs, 2 no epilogue math, 4 no map flush
 };
-// tmQ: split qkv [B*N, 6D], box 64 x 128 rows; tmV: split V^T [B*D, 2*np], box 64 keys x 64 rows
-int attn_pv(const CUtensorMap& tmQ, const CUtensorMap& tmV, const AttnPvParams& p, cudaStream_t st);
+// tmQ: split qkv [B*N, 6D], box 64 x 128 rows (V is consumed in place as an MN-major B operand: no transpose)
+int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st);
 // dense [rows, N] <- padded [rows, Npad]
 int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st);
 

@@ -91,6 +91,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int bn) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
+// same with an MN-major B operand (bit 16): the B tile is stored [K rows][N contiguous], e.g. V [keys, head dim] as it sits
+// in the qkv matrix.  With 64 fp16 along N (one 128 B swizzle atom) the shared-memory descriptor is the K-major one
+// (8-row groups 1024 B apart); a 16-element K step advances the start address by 16 rows = 2048 B.
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int bn) { return make_idesc(bn) | (1u << 16); }
 
 
 }  // namespace xl

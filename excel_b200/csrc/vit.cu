@@ -216,18 +216,19 @@ static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
     const int qx[1] = {0}, ky[1] = {c.D};
     if (int e = scores(c, 1, qx, ky, scale, nullptr, 0.f, true)) return e;
     AttnPvParams q = {};
-    q.B = c.B; q.H = c.H; q.N = c.N; q.np = c.np; q.D = c.D; q.xo = 0; q.yo = c.D; q.lo_off = 3 * c.D;
+    q.B = c.B; q.H = c.H; q.N = c.N; q.D = c.D; q.xo = 0; q.yo = c.D; q.vo = 2 * c.D; q.lo_off = 3 * c.D;
     q.alpha = scale * 1.4426950408889634f; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
     static const int dbg = getenv("EXCEL_PV_DBG") ? atoi(getenv("EXCEL_PV_DBG")) : 0;   // timing experiments only
     q.dbg = dbg;
-    if (int e = attn_pv(c.m.qkv_a, c.m.vt64, q, c.st)) return e;
+    if (int e = attn_pv(c.m.qkv_a, q, c.st)) return e;
     return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);   // API layout [B,N,N]
 }
 
-// ln_1 -> in_proj -> split qkv, V^T
-static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in) {
+// ln_1 -> in_proj -> split qkv (, V^T)
+static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in, bool need_vt) {
     if (int e = layernorm(c, src, Lw.ln1_w, Lw.ln1_b, c.w.h)) return e;
     if (int e = linear(c, c.m.h, m_in, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv)) return e;
+    if (!need_vt) return 0;   // the fused attention reads V in place; only the surgery new-path GEMM wants V^T
     dim3 grid(ceil_div(c.np, 32), c.D / 32, c.B), block(32, 32);
     vt_kernel<<<grid, block, 0, c.st>>>(c.w.qkv, c.N, c.D, c.np, c.w.vt);
     return check_launch("vt_kernel");
@@ -351,7 +352,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* attn_l = attn + (int64_t)l * B * N * N;
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
-            if (int e = qkv_stage(c, x, Lw, m_in)) return e;
+            if (int e = qkv_stage(c, x, Lw, m_in, false)) return e;
             if (int e = attention_qk(c, scale, attn_l, 1.f / H)) return e;    // need_weights: head mean; o = attn @ v
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
@@ -359,7 +360,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         } else {  // ---- surgery block (:309-330, Attention.forward :95-159)
             float* xnew = feats + (int64_t)(first - 1) * BN * D;              // new path, accumulates x_res in place
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
-            if (int e = qkv_stage(c, src, Lw, m_in)) return e;
+            if (int e = qkv_stage(c, src, Lw, m_in, true)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
             if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, false)) return e;
             if (int e = split_f16(c.w.pnew, (N + 3) & ~3, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
