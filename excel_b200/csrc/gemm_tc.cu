@@ -110,11 +110,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_arrive_expect_tx(&full_bar[s], kTxBytes);
                     tma_load_2d(st, &tmA, &full_bar[s], a_col + kb * kBK, a_row);
                     tma_load_2d(st + kTileBytes, &tmA, &full_bar[s], a_col + p.a_lo_off + kb * kBK, a_row);
-                    // B tiles wider than 128 rows arrive as stacked 128-row boxes (the operand maps keep a 128-row box)
+                    if (p.b_mn) {
+                        // MN-major B: 64-column x 64-row boxes, one per 64 columns of the tile (b_row / b_col then hold the
+                        // K row / N column of the tile: n0 moves along the columns)
 #pragma unroll
-                    for (int r = 0; r < kBN; r += 128) {
-                        tma_load_2d(st + 2 * kTileBytes + r * 128, &tmB, &full_bar[s], b_col + kb * kBK, b_row + r);
-                        tma_load_2d(st + 2 * kTileBytes + kBBytes + r * 128, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row + r);
+                        for (int c = 0; c < kBN; c += 64) {
+                            tma_load_2d(st + 2 * kTileBytes + c * 128, &tmB, &full_bar[s], b_col + n0 + c, b_row - n0 + kb * kBK);
+                            tma_load_2d(st + 2 * kTileBytes + kBBytes + c * 128, &tmB, &full_bar[s], b_col + n0 + c + p.b_lo_off,
+                                        b_row - n0 + kb * kBK);
+                        }
+                    } else {
+                        // B tiles wider than 128 rows arrive as stacked 128-row boxes (the operand maps keep a 128-row box)
+#pragma unroll
+                        for (int r = 0; r < kBN; r += 128) {
+                            tma_load_2d(st + 2 * kTileBytes + r * 128, &tmB, &full_bar[s], b_col + kb * kBK, b_row + r);
+                            tma_load_2d(st + 2 * kTileBytes + kBBytes + r * 128, &tmB, &full_bar[s], b_col + p.b_lo_off + kb * kBK, b_row + r);
+                        }
                     }
                 }
             }
@@ -134,14 +145,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t st = tiles0 + s * kStageBytes;
                 const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileBytes);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * kTileBytes), b_lo = umma_desc_sw128(st + 2 * kTileBytes + kBBytes);
+                // K-major B: a 16-element K step is 32 B inside the swizzle atom; MN-major B: 16 rows = 2048 B, atoms along N 8 KB apart
+                const uint64_t b_hi = p.b_mn ? umma_desc_sw128_mn(st + 2 * kTileBytes, 8192) : umma_desc_sw128(st + 2 * kTileBytes);
+                const uint64_t b_lo = p.b_mn ? umma_desc_sw128_mn(st + 2 * kTileBytes + kBBytes, 8192)
+                                             : umma_desc_sw128(st + 2 * kTileBytes + kBBytes);
+                const uint64_t b_step = p.b_mn ? 128 : 2;
+                const uint32_t idesc = p.b_mn ? make_idesc_bmn(kBN) : kIdesc;
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < kBK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 16 fp16 = 32 B further along K inside the swizzle atom
-                        umma_f16(tacc, a_hi + adv, b_lo + adv, kIdesc, (kb | k) != 0);
-                        umma_f16(tacc, a_lo + adv, b_hi + adv, kIdesc, 1);
-                        umma_f16(tacc, a_hi + adv, b_hi + adv, kIdesc, 1);
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);  // A: 16 fp16 = 32 B further along K inside the swizzle atom
+                        umma_f16(tacc, a_hi + adv, b_lo + k * b_step, idesc, (kb | k) != 0);
+                        umma_f16(tacc, a_lo + adv, b_hi + k * b_step, idesc, 1);
+                        umma_f16(tacc, a_hi + adv, b_hi + k * b_step, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);  // stage s may be refilled once these MMAs have read it
                 }

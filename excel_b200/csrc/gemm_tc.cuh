@@ -25,6 +25,8 @@ struct TcParams {
     __half* Cs;                 // split-fp16 output (may be null): hi at Cs, lo at Cs + cs_lo_off
     int64_t lds, cs1, cs2;
     int cs_lo_off;
+    int b_mn;                   // B is stored [K rows, N columns] (MN-major, e.g. V inside the qkv matrix): b_row* address the K
+                                // dimension, b_col* the N dimension; its tensor map has a 64-column x 64-row box
 };
 
 // tensor map of a split-fp16 operand [rows, cols_total] with row pitch ld_elems (box 64 k x box_rows, SWIZZLE_128B);

@@ -115,32 +115,6 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
-// ---- V^T: vt[(b*D + c), token] from the V block of qkv_s, split halves, zero padded to np tokens -------------
-__global__ void __launch_bounds__(1024)
-vt_kernel(const __half* __restrict__ qkv, int N, int D, int np, __half* __restrict__ vt) {
-    __shared__ __half th[32][33], tl[32][33];
-    const int b = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    {
-        const int n = n0 + ty, c = c0 + tx;
-        __half h = __float2half_rn(0.f), l = h;
-        if (n < N) {
-            const __half* r = qkv + ((int64_t)b * N + n) * 6 * D;
-            h = r[2 * D + c];
-            l = r[3 * D + 2 * D + c];
-        }
-        th[ty][tx] = h;
-        tl[ty][tx] = l;
-    }
-    __syncthreads();
-    const int c = c0 + ty, n = n0 + tx;
-    if (n < np) {
-        __half* o = vt + ((int64_t)b * D + c) * 2 * np;
-        o[n] = th[tx][ty];
-        o[np + n] = tl[tx][ty];
-    }
-}
-
 __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t stride_b, int D) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (d < D) dst[(int64_t)b * stride_b + d] = src[(int64_t)b * stride_b + d];
@@ -148,7 +122,7 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 
 struct Ws {  // workspace carve-up
     float *pos, *m, *pnew, *pad, *mid, *x0;
-    __half *col, *h, *qkv, *vt, *pn, *o, *o2, *u;
+    __half *col, *h, *qkv, *pn, *o, *o2, *u;
 };
 
 static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
@@ -163,14 +137,13 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
     t += 3 * align256(BN * 2 * D * 2);                // h, o, o2
     t += align256(BN * 6 * D * 2);                    // qkv
-    t += align256((size_t)B * D * 2 * np * 2);        // vt
     t += align256(BN * 2 * np * 2);                   // pn
     t += align256(BN * 8 * D * 2);                    // u
     return t + 256;
 }
 
 struct Maps {  // tensor maps of the activation operands (built once per forward)
-    CUtensorMap col, h, qkv_a, qkv_b, vt64, vt128, pn, o, o2, u;
+    CUtensorMap col, h, qkv_a, qkv_v, pn, o, o2, u;
 };
 
 struct Ctx {
@@ -224,14 +197,10 @@ static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
     return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);   // API layout [B,N,N]
 }
 
-// ln_1 -> in_proj -> split qkv (, V^T)
-static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in, bool need_vt) {
+// ln_1 -> in_proj -> split qkv (V is consumed in place, MN-major, by the attention kernel and the new-path GEMM)
+static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in) {
     if (int e = layernorm(c, src, Lw.ln1_w, Lw.ln1_b, c.w.h)) return e;
-    if (int e = linear(c, c.m.h, m_in, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv)) return e;
-    if (!need_vt) return 0;   // the fused attention reads V in place; only the surgery new-path GEMM wants V^T
-    dim3 grid(ceil_div(c.np, 32), c.D / 32, c.B), block(32, 32);
-    vt_kernel<<<grid, block, 0, c.st>>>(c.w.qkv, c.N, c.D, c.np, c.w.vt);
-    return check_launch("vt_kernel");
+    return linear(c, c.m.h, m_in, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv);
 }
 
 // feat = mid + c_proj(QuickGELU(c_fc(ln_2(mid))))
@@ -293,7 +262,6 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         c.w.o = (__half*)take(BN * 2 * D * 2);
         c.w.o2 = (__half*)take(BN * 2 * D * 2);
         c.w.qkv = (__half*)take(BN * 6 * D * 2);
-        c.w.vt = (__half*)take((size_t)B * D * 2 * np * 2);
         c.w.pn = (__half*)take(BN * 2 * np * 2);
         c.w.u = (__half*)take(BN * 8 * D * 2);
     }
@@ -302,9 +270,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         e |= make_operand_map(&c.m.col, c.w.col, (int64_t)B * npatch, 2 * KKp, 2 * KKp, 128);
         e |= make_operand_map(&c.m.h, c.w.h, BN, 2 * D, 2 * D, 128);
         e |= make_operand_map(&c.m.qkv_a, c.w.qkv, BN, 6 * D, 6 * D, 128);
-        e |= make_operand_map(&c.m.qkv_b, c.w.qkv, BN, 6 * D, 6 * D, 128);
-        e |= make_operand_map(&c.m.vt64, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 64);
-        e |= make_operand_map(&c.m.vt128, c.w.vt, (int64_t)B * D, 2 * np, 2 * np, 128);
+        e |= make_operand_map(&c.m.qkv_v, c.w.qkv, BN, 6 * D, 6 * D, 64);   // 64 x 64 boxes: MN-major B operand (V)
         e |= make_operand_map(&c.m.pn, c.w.pn, BN, 2 * np, 2 * np, 128);
         e |= make_operand_map(&c.m.o, c.w.o, BN, 2 * D, 2 * D, 128);
         e |= make_operand_map(&c.m.o2, c.w.o2, BN, 2 * D, 2 * D, 128);
@@ -352,7 +318,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         float* attn_l = attn + (int64_t)l * B * N * N;
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
-            if (int e = qkv_stage(c, x, Lw, m_in, false)) return e;
+            if (int e = qkv_stage(c, x, Lw, m_in)) return e;
             if (int e = attention_qk(c, scale, attn_l, 1.f / H)) return e;    // need_weights: head mean; o = attn @ v
             if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
             if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
@@ -360,16 +326,17 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         } else {  // ---- surgery block (:309-330, Attention.forward :95-159)
             float* xnew = feats + (int64_t)(first - 1) * BN * D;              // new path, accumulates x_res in place
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
-            if (int e = qkv_stage(c, src, Lw, m_in, true)) return e;
+            if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
             if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, false)) return e;
             if (int e = split_f16(c.w.pnew, (N + 3) & ~3, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
-                p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.b_lo_off = np; p.nb2 = 1;
-                p.a_row1 = N; p.b_row1 = D; p.alpha = 1.f / kProbScale;
+                // B operand = V [keys, D] in place inside the split qkv matrix (MN-major): no transpose pass
+                p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.nb2 = 1;
+                p.a_row1 = N; p.b_mn = 1; p.b_row1 = N; p.b_col0 = 2 * D; p.b_lo_off = 3 * D; p.alpha = 1.f / kProbScale;
                 p.Cs = c.w.o2; p.lds = 2 * D; p.cs1 = (int64_t)N * 2 * D; p.cs_lo_off = D;
-                if (int e = tc_gemm(c.m.pn, c.m.vt128, p, B, 128, st)) return e;
+                if (int e = tc_gemm(c.m.pn, c.m.qkv_v, p, B, D % 256 == 0 ? 256 : 128, st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
             if (int e = attention_qk(c, scale, attn_l, 1.f)) return e;          // x_ori = attn_ori @ v
