@@ -34,7 +34,10 @@ SIGNATURES = {
     "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _p, _p], _i),
     "excel_vit_workspace_bytes": ([_i, _i, _i, _i, _i], _i64),
     "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
-    "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p], _i),
+    "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p], _i),
+    "excel_lvc_attention": ([_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p], _i),
+    "excel_row_softmax": ([_p, _i, _i, _p, _p], _i),
+    "excel_row_l2_normalize": ([_p, _i, _i, _p, _p], _i),
     "excel_gemm_tc": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _p], _i),
     "excel_radius_mask": ([_i, _i, _i, _p, _p], _i),
     "excel_affinity_label": ([_p, _i, _i, _i, _i, _i, _p, _i64, _p, _p], _i),

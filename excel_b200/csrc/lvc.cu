@@ -1,0 +1,133 @@
+// LVC bias of the surgery attention (reference: clip/clip_surgery_model.py:127-141, Attention.forward with ex_feats) and
+// the small row-wise helpers of utils/attrutils.py.
+//
+//   ex_attn[b] = softmax_j( mask_{<0 -> -inf}( (cos_sim(f_b)[i,j] - mean_over_batch(cos_sim)) * gamma ) ),
+//   f_b = decoder features [C, n_p] L2-normalised over C per position (F.normalize, eps 1e-12).
+// The reference adds ex_attn to EVERY head's patch block of the new-path attention and then sums the heads (:139-146), so
+// the encoder adds H * ex_attn to the head-summed map (vit.cu).  The similarity is an exact fp32 SIMT GEMM (gemm_simt.cu);
+// the batch-wide mean is accumulated in double in a fixed order (the threshold at 0 right next to it is discontinuous).
+#include "common.cuh"
+#include "excel_b200.h"
+
+namespace xl {
+
+// qt[b, m, c] = f[b, c, m] / max(||f[b, :, m]||, 1e-12): normalise over channels and transpose to [n_p, C]
+__global__ void lvc_normalize_t_kernel(const float* __restrict__ f, int C, int np, float* __restrict__ qt) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (m >= np) return;
+    const float* src = f + (int64_t)b * C * np + m;
+    float ss = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float v = src[(int64_t)c * np];
+        ss = fmaf(v, v, ss);
+    }
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float* dst = qt + ((int64_t)b * np + m) * C;
+    for (int c = 0; c < C; ++c) dst[c] = src[(int64_t)c * np] * inv;
+}
+
+// rowsum[r] = sum_j x[r, j] in double, one warp per row
+__global__ void __launch_bounds__(256)
+row_sum_f64_kernel(const float* __restrict__ x, int64_t rows, int cols, double* __restrict__ rowsum) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    double s = 0.0;
+    for (int j = lane; j < cols; j += 32) s += (double)x[row * cols + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) rowsum[row] = s;
+}
+
+// mean[0] = sum(rowsum) / count, one block, fixed order
+__global__ void __launch_bounds__(1024)
+total_mean_kernel(const double* __restrict__ rowsum, int64_t rows, double count, float* __restrict__ mean) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < rows; i += 1024) s += rowsum[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) mean[0] = (float)(s / count);
+    }
+}
+
+// out[r, :] = softmax_j(t(x[r, :])), t(v) = v (plain) or ((v - mean*beta) * gamma, negatives -> -inf); one warp per row.
+// A row whose entries are all masked gives NaN like torch.softmax of an all -inf row.
+template <bool MASKED>
+__global__ void __launch_bounds__(256)
+row_softmax_kernel(const float* __restrict__ x, int64_t rows, int cols, const float* __restrict__ mean, float beta, float gamma,
+                   float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const float* xr = x + row * cols;
+    float* yr = out + row * cols;
+    const float sub = MASKED ? mean[0] * beta : 0.f;
+    auto tr = [&](float v) {
+        if (!MASKED) return v;
+        const float t = (v - sub) * gamma;
+        return t < 0.f ? -INFINITY : t;
+    };
+    float mx = -INFINITY;
+    for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, tr(xr[j]));
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int j = lane; j < cols; j += 32) s += expf(tr(xr[j]) - mx);
+    s = warp_sum(s);
+    for (int j = lane; j < cols; j += 32) yr[j] = expf(tr(xr[j]) - mx) / s;
+}
+
+__global__ void __launch_bounds__(256)
+row_l2_normalize_kernel(const float* __restrict__ x, int64_t rows, int cols, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float ss = 0.f;
+    for (int j = lane; j < cols; j += 32) ss = fmaf(x[row * cols + j], x[row * cols + j], ss);
+    const float n = sqrtf(warp_sum(ss));
+    for (int j = lane; j < cols; j += 32) out[row * cols + j] = x[row * cols + j] / n;
+}
+
+}  // namespace xl
+
+using namespace xl;
+
+extern "C" int excel_row_softmax(const float* x, int rows, int cols, float* out, void* stream) {
+    XL_REQUIRE(rows >= 0 && cols >= 1, "row_softmax: bad shape");
+    if (rows == 0) return 0;
+    row_softmax_kernel<false><<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, nullptr, 0.f, 1.f, out);
+    return check_launch("row_softmax_kernel");
+}
+
+extern "C" int excel_row_l2_normalize(const float* x, int rows, int cols, float* out, void* stream) {
+    XL_REQUIRE(rows >= 0 && cols >= 1, "row_l2_normalize: bad shape");
+    if (rows == 0) return 0;
+    row_l2_normalize_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, out);
+    return check_launch("row_l2_normalize_kernel");
+}
+
+extern "C" int excel_lvc_attention(const float* ex_feats, int B, int C, int np, float beta, float gamma, float* qt_ws,
+                                   double* rowsum_ws, float* mean_ws, float* ex_attn, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    XL_REQUIRE(B >= 0 && C >= 1 && np >= 1 && B <= 65535, "lvc_attention: bad shape B=%d C=%d np=%d", B, C, np);
+    XL_REQUIRE(ex_feats && qt_ws && rowsum_ws && mean_ws && ex_attn, "lvc_attention: missing buffers");
+    if (B == 0) return 0;
+    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 128), B), 128, 0, st>>>(ex_feats, C, np, qt_ws);
+    if (int e = check_launch("lvc_normalize_t_kernel")) return e;
+    // sim[b] = qt[b] qt[b]^T  (exact fp32), written into ex_attn and transformed in place row by row
+    if (int e = sgemm2(qt_ws, qt_ws, ex_attn, nullptr, nullptr, np, np, C, C, C, np, B, (int64_t)np * C, (int64_t)np * C,
+                       (int64_t)np * np, 1, 0, 0, 0, 1.f, 1, 0, st)) return e;
+    const int64_t rows = (int64_t)B * np;
+    row_sum_f64_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(ex_attn, rows, np, rowsum_ws);
+    if (int e = check_launch("row_sum_f64_kernel")) return e;
+    total_mean_kernel<<<1, 1024, 0, st>>>(rowsum_ws, rows, (double)rows * np, mean_ws);
+    if (int e = check_launch("total_mean_kernel")) return e;
+    row_softmax_kernel<true><<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(ex_attn, rows, np, mean_ws, beta, gamma, ex_attn);
+    return check_launch("row_softmax_kernel<masked>");
+}

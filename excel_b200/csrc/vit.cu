@@ -115,6 +115,13 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
+// pnew[b, 1+i, 1+j] += coef * ex_attn[b, i, j]  (row-padded map, pitch npad)
+__global__ void lvc_add_kernel(const float* __restrict__ ex_attn, int np, float coef, float* __restrict__ pnew, int npad, int N) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
+    if (j >= np) return;
+    pnew[((int64_t)b * N + 1 + i) * npad + 1 + j] += coef * ex_attn[((int64_t)b * np + i) * np + j];
+}
+
 __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t stride_b, int D) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (d < D) dst[(int64_t)b * stride_b + d] = src[(int64_t)b * stride_b + d];
@@ -226,7 +233,7 @@ extern "C" int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, 
 
 extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, int64_t img_stride_b, int64_t img_stride_c,
                                  int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes,
-                                 float* tokens, float* attn, float* feats, void* stream) {
+                                 float* tokens, float* attn, float* feats, const float* lvc_attn, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     XL_REQUIRE(Wt != nullptr, "vit_forward: null weights");
     const int L = Wt->layers, D = Wt->width, H = Wt->heads, P = Wt->patch, E = Wt->embed, g0 = Wt->grid0,
@@ -329,6 +336,11 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             if (int e = qkv_stage(c, src, Lw, m_in)) return e;
             // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
             if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, false)) return e;
+            if (lvc_attn) {   // LVC: + ex_attn on every head's patch block, then summed over heads (:139-146) == + H * ex_attn
+                dim3 grid(ceil_div(N - 1, 256), N - 1, B);
+                lvc_add_kernel<<<grid, 256, 0, st>>>(lvc_attn, N - 1, (float)H, c.w.pnew, (N + 3) & ~3, N);
+                if (int e = check_launch("lvc_add_kernel")) return e;
+            }
             if (int e = split_f16(c.w.pnew, (N + 3) & ~3, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};

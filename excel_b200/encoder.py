@@ -44,8 +44,14 @@ def pack_from_visual(visual):
 class SurgeryViT:
     """Frozen CLIP-surgery ViT.  ``weights``: pack as produced by ``pack_from_visual`` (any device)."""
 
-    def __init__(self, weights, n_surgery=5, device="cuda"):
+    def __init__(self, weights, n_surgery=5, device="cuda", graph=False):
         self.device = torch.device(device)
+        # graph=True: the ~190 launches of a forward are captured once per input shape into a CUDA graph and replayed
+        # (no host launch gaps).  The three output tensors are then REUSED by every call with that shape -- meant for
+        # pipelines that consume them before the next forward (pipeline.ExCELHotPath), not for the drop-in shims.
+        self.graph = graph
+        self._graphs = {}
+        self.replayed_launches = 0
         L, H, P = (int(v) for v in weights["meta"])
         self.W = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in weights.items() if k != "meta"}
         self.layers, self.heads, self.patch, self.n_surgery = L, H, P, n_surgery
@@ -90,8 +96,10 @@ class SurgeryViT:
         return cls(pack_from_visual(visual), n_surgery, device)
 
     @torch.no_grad()
-    def forward(self, img):
-        """img [B,3,S,S] -> (tokens [B,N,E] un-normalised, attn [L,B,N,N], feats [L,B,N,D])."""
+    def forward(self, img, ex_feats=None):
+        """img [B,3,S,S] -> (tokens [B,N,E] un-normalised, attn [L,B,N,N], feats [L,B,N,D]).
+        ex_feats [B,C,h,w] (decoder features, h*w = N-1): LVC branch of the surgery attention
+        (clip/clip_surgery_model.py:127-141)."""
         img = img.to(self.device, torch.float32)
         if img.stride(-1) != 1:
             img = img.contiguous()
@@ -100,6 +108,33 @@ class SurgeryViT:
             raise RuntimeError(f"SurgeryViT: expected [B,3,S,S] square images, got {tuple(img.shape)}")
         if S % self.patch:
             raise RuntimeError(f"SurgeryViT: image size {S} is not a multiple of the patch size {self.patch}")
+        if ex_feats is not None:
+            return self._forward(img, lvc_attention(ex_feats, (S // self.patch) ** 2))
+        if self.graph:
+            return self._forward_graph(img)
+        return self._forward(img)
+
+    def _forward_graph(self, img):
+        key = tuple(img.shape)
+        g = self._graphs.get(key)
+        if g is None:
+            static_in = torch.empty_like(img)
+            static_in.copy_(img)
+            self._forward(static_in)                      # warm-up outside the capture (function attributes, workspace)
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().excel_launch_count()
+            with torch.cuda.graph(graph):
+                outs = self._forward(static_in)
+            g = self._graphs[key] = (graph, static_in, outs, _lib.lib().excel_launch_count() - n0)
+        graph, static_in, outs, nlaunch = g
+        static_in.copy_(img)
+        graph.replay()
+        self.replayed_launches += nlaunch      # kernels launched by graph replays (the library's counter sees host launches only)
+        return outs
+
+    def _forward(self, img, lvc_attn=None):
+        B, C, S, S2 = img.shape
         N = (S // self.patch) ** 2 + 1
         nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
         if self._ws is None or self._ws.numel() * 4 < nbytes:
@@ -109,10 +144,29 @@ class SurgeryViT:
         attn = torch.empty((self.layers, B, N, N), dtype=torch.float32, device=self.device)
         feats = torch.empty((self.layers, B, N, self.width), dtype=torch.float32, device=self.device)
         _lib.call("excel_vit_forward", ctypes.byref(self._w), _lib.ptr(img), img.stride(0), img.stride(1), img.stride(2), B, S,
-                  _lib.ptr(self._ws), self._ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.stream())
+                  _lib.ptr(self._ws), self._ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.ptr(lvc_attn),
+                  _lib.stream())
         return tokens, attn, feats
 
     __call__ = forward
+
+
+def lvc_attention(ex_feats, n_p=None, beta=1.0, gamma=3.0):
+    """clip/clip_surgery_model.py:127-137: decoder features [B,C,h,w] -> ex_attn [B,n_p,n_p] (fp32, CUDA)."""
+    f = _lib.f32c(ex_feats)
+    B, C = f.shape[:2]
+    f = f.reshape(B, C, -1)
+    np_ = f.shape[2]
+    if n_p is not None and np_ != n_p:
+        raise RuntimeError(f"ex_feats has {np_} positions, the encoder has {n_p} patches")
+    dev = f.device
+    qt = torch.empty((B, np_, C), dtype=torch.float32, device=dev)
+    rowsum = torch.empty((B * np_,), dtype=torch.float64, device=dev)
+    mean = torch.empty((1,), dtype=torch.float32, device=dev)
+    out = torch.empty((B, np_, np_), dtype=torch.float32, device=dev)
+    _lib.call("excel_lvc_attention", _lib.ptr(f), B, C, np_, float(beta), float(gamma), _lib.ptr(qt), _lib.ptr(rowsum),
+              _lib.ptr(mean), _lib.ptr(out), _lib.stream())
+    return out
 
 
 _ENGINES = {}
@@ -134,7 +188,5 @@ def engine_for(model, n_surgery=5):
 def generate_clip_fts(inputs, model, return_weights=True, ex_feats=None):
     """clip/clip.py:348-358: (image_features [B,N,E] normalised over the TOKEN axis, attn_weights [L,B,N,N],
     all_feats [L,B,N,D]).  ``model``: a SurgeryViT, or the reference's ExCEL_CLIP module."""
-    if ex_feats is not None:
-        raise NotImplementedError("excel_b200: generate_clip_fts(ex_feats=...) (LVC branch) is SURVEY §8(f1), not built yet")
-    tokens, attn, feats = engine_for(model)(inputs)
+    tokens, attn, feats = engine_for(model)(inputs, ex_feats)
     return token_normalize(tokens), attn, feats

@@ -4,8 +4,7 @@ engine/validatation_engine.py) run on the sm_100a hot path WITHOUT editing them.
 The reference has no plugin API; its boundary is a set of module-level Python functions imported by name
 (SURVEY.md §8b).  ``install()`` imports those reference modules and rebinds the hot-path symbols to this
 package's implementations, so that a later ``from utils.affutils import refine_cams_with_aff`` in a script binds
-ours.  The one branch this round has not built (the LVC ``ex_feats`` path of the encoder) keeps
-dispatching to the reference's own PyTorch code.
+ours -- both branches of every function (training-free and LVC: ``ex_feats`` in the encoder, ``seg_attn`` in SVC).
 
     python -m excel_b200.run tools/infer_lam.py --infer_set train --training_free true ...
 """
@@ -20,7 +19,7 @@ def install(reference_root=None):
         reference_root = os.path.abspath(reference_root)
         if reference_root not in sys.path:
             sys.path.insert(0, reference_root)
-    from . import affutils as my_aff, camutils as my_cam, clip as my_clip, encoder as my_enc, par as my_par
+    from . import affutils as my_aff, attrutils as my_attr, camutils as my_cam, clip as my_clip, encoder as my_enc, par as my_par
 
     originals = {}
 
@@ -39,17 +38,10 @@ def install(reference_root=None):
     patch("utils.camutils", "cams_to_affinity_label", my_cam.cams_to_affinity_label)
     patch("utils.camutils", "get_mask_by_radius", my_cam.get_mask_by_radius)
 
-    ref_clip = importlib.import_module("clip")
-    ref_clip_inner = importlib.import_module("clip.clip")
-    ref_gen = ref_clip_inner.generate_clip_fts
-
-    def generate_clip_fts(inputs, model, return_weights=True, ex_feats=None):
-        if ex_feats is not None:      # LVC branch: reference implementation
-            return ref_gen(inputs, model, return_weights, ex_feats)
-        return my_enc.generate_clip_fts(inputs, model, return_weights)
-
+    patch("utils.attrutils", "attrmap2clsmap", my_attr.attrmap2clsmap)
+    patch("utils.attrutils", "attr2cls_embedings", my_attr.attr2cls_embedings)
     for mod in ("clip", "clip.clip"):
-        patch(mod, "generate_clip_fts", generate_clip_fts)
+        patch(mod, "generate_clip_fts", my_enc.generate_clip_fts)
         patch(mod, "clip_feature_surgery", my_clip.clip_feature_surgery)
     return originals
 

@@ -138,10 +138,22 @@ int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, voi
 /* VisionTransformer.forward + Transformer.forward (clip/clip_surgery_model.py:418-448, 346-371) as called by
  * clip.generate_clip_fts (clip/clip.py:348-358), for img [B,3,S,S] (element strides b, c, y; x contiguous).
  * Outputs: tokens [B,N,embed] (BEFORE the token-axis normalisation of clip.py:353 -> excel_token_normalize),
- * attn [layers,B,N,N], feats [layers,B,N,width] with the reference's view aliasing. */
+ * attn [layers,B,N,N], feats [layers,B,N,width] with the reference's view aliasing.
+ * lvc_attn: NULL, or the LVC bias ex_attn [B,N-1,N-1] of excel_lvc_attention (Attention.forward with ex_feats,
+ * clip/clip_surgery_model.py:127-141): added to every head's patch block of the surgery blocks' new-path attention. */
 int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_stride_b, int64_t img_stride_c,
                       int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes, float* tokens,
-                      float* attn, float* feats, void* stream);
+                      float* attn, float* feats, const float* lvc_attn, void* stream);
+
+/* clip/clip_surgery_model.py:127-137: ex_feats [B,C,np] (decoder features, np = h*w positions) -> ex_attn [B,np,np] =
+ * softmax_j of ((cosine similarity - mean over the WHOLE batch * beta) * gamma) with negatives set to -inf.
+ * Workspaces: qt_ws [B*np*C] floats, rowsum_ws [B*np] doubles, mean_ws [1] float. */
+int excel_lvc_attention(const float* ex_feats, int B, int C, int np, float beta, float gamma, float* qt_ws,
+                        double* rowsum_ws, float* mean_ws, float* ex_attn, void* stream);
+
+/* utils/attrutils.py helpers: out[r,:] = softmax(x[r,:]) / x[r,:] / ||x[r,:]||_2 for x [rows, cols]. */
+int excel_row_softmax(const float* x, int rows, int cols, float* out, void* stream);
+int excel_row_l2_normalize(const float* x, int rows, int cols, float* out, void* stream);
 
 /* ---------------------------------------------------------------- metric (utils/evaluate.py) --- */
 

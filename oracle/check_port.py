@@ -54,6 +54,26 @@ def main():
     attr = port.clip_feature_surgery(tok, text_t)[:, 1:, :num_fg]
     gate("clip_feature_surgery (attr_maps_raw)", (attr - attr_ref).abs().max().item(), 5e-5)
 
+    # ---- LVC branch: ExCEL_model.forward(img, ex_feats=attn_fts) -> attr_maps_raw only (model_excel.py:50-53)
+    attr_lvc_ref = model(imgs, ex_feats=attn_fts)
+    tok_l, attn_l, feats_l = port.generate_clip_fts(W, imgs, ex_feats=attn_fts)
+    attr_lvc = port.clip_feature_surgery(tok_l, text_t)[:, 1:, :num_fg]
+    gate("LVC: model(img, ex_feats) attr_maps_raw", (attr_lvc - attr_lvc_ref).abs().max().item(), 5e-5)
+    tok_lr, attn_lr, feats_lr = ref.clip.generate_clip_fts(imgs, enc, return_weights=True, ex_feats=attn_fts)
+    gate("LVC: generate_clip_fts.image_features", (tok_l - tok_lr).abs().max().item(), 2e-5)
+    gate("LVC: generate_clip_fts.all_feats", (feats_l - feats_lr).abs().max().item(), 2e-4)
+    print(f"       LVC bias changes attr_maps_raw by up to {(attr_lvc_ref - attr_ref).abs().max().item():.3e}")
+
+    # ---- attrutils (a10): no live caller in the reference, checked function by function
+    gA = torch.Generator().manual_seed(9)
+    flag = (torch.rand(20, 112, generator=gA) > 0.8).float()
+    amap = torch.rand(2, 49, 112, generator=gA)
+    gate("attrutils.attrmap2clsmap", (ref.attrutils.attrmap2clsmap(flag, amap) - port.attrmap2clsmap(flag, amap)).abs().max().item(), 1e-6)
+    tf = torch.randn(20, 64, generator=gA)
+    bank = torch.randn(64, 112, generator=gA)
+    gate("attrutils.attr2cls_embedings (no bg rows)",
+         (ref.attrutils.attr2cls_embedings(tf, bank, 20) - port.attr2cls_embedings(tf, bank, 20)).abs().max().item(), 1e-6)
+
     # ---- SVC + PAR per image, on the REFERENCE's encoder outputs (stage isolation)
     par = ref.PAR(num_iter=20, dilations=list(port.PAR_DILATIONS))
     mism = 0

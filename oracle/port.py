@@ -99,8 +99,18 @@ def _std_attention(x, W, o, H):
     return out, p.mean(dim=1)
 
 
-def _surgery_attention(x, W, o, H):
-    """Surgery ``Attention.forward`` with ex_feats=None (clip/clip_surgery_model.py:95-159).
+def lvc_attention(ex_feats, beta=1.0, gamma=3.0):
+    """LVC bias of the surgery attention (clip/clip_surgery_model.py:127-136): ex_feats [B,C,h,w] decoder features ->
+    ex_attn [B,n_p,n_p] = softmax_j of the batch-mean-centred, x3, negatives -> -inf cosine similarity."""
+    q_k = F.normalize(ex_feats.flatten(2, 3).float(), dim=1)                   # :130
+    sim = torch.einsum("bcm,bcn->bmn", q_k, q_k)                               # :131
+    sim = (sim - torch.mean(sim) * beta) * gamma                               # :132 (mean over the WHOLE batch)
+    sim = sim.masked_fill(sim < 0.0, float("-inf"))                            # :133
+    return torch.softmax(sim, dim=-1)                                          # :137 (same for every head)
+
+
+def _surgery_attention(x, W, o, H, ex_attn=None):
+    """Surgery ``Attention.forward`` (clip/clip_surgery_model.py:95-159); ex_attn = lvc_attention(ex_feats) or None.
     Returns (x_new, x_ori, attn_ori head-SUM)."""
     B, N, D = x.shape
     scale = (D // H) ** -0.5
@@ -110,6 +120,9 @@ def _surgery_attention(x, W, o, H):
     p_new = (torch.softmax((q @ q.transpose(-1, -2)) * scale, dim=-1)
              + torch.softmax((k @ k.transpose(-1, -2)) * scale, dim=-1)
              + torch.softmax((v @ v.transpose(-1, -2)) * scale, dim=-1)) / 3   # :119-125
+    if ex_attn is not None:                                                    # :139-141 added to every head's patch block
+        p_new = p_new.clone()
+        p_new[:, :, 1:, 1:] = p_new[:, :, 1:, 1:] + ex_attn.unsqueeze(1)
     p_new = p_new.sum(dim=1, keepdim=True)                                     # :146 (sum over heads)
     x_ori = (p_ori @ v).permute(0, 2, 1, 3).reshape(B, N, D)                   # :148
     x_new = (p_new @ v).permute(0, 2, 1, 3).reshape(B, N, D)                   # :149
@@ -130,7 +143,7 @@ def resize_pos_embed(pos, new_side):
     return torch.cat([pos[:1], grid], 0)
 
 
-def vit_forward(W, img, n_surgery=5):
+def vit_forward(W, img, n_surgery=5, ex_feats=None):
     """VisionTransformer.forward + Transformer.forward (clip/clip_surgery_model.py:418-448,346-371)
     for a [B,3,S,S] image batch.  Returns (tokens [B,N,E] BEFORE the token-axis normalisation,
     attn list of L x [B,N,N], feats list of L x [B,N,D] with the aliasing of row a5 applied)."""
@@ -144,6 +157,7 @@ def vit_forward(W, img, n_surgery=5):
     x = _layer_norm(x, W["ln_pre.weight"], W["ln_pre.bias"])         # :438
     attns, feats = [], []
     first = L - n_surgery                                            # :399 range(1, layers) -> last 5 blocks
+    ex_attn = None if ex_feats is None else lvc_attention(ex_feats)
     x_ori = None
     for i in range(L):
         o = "blocks.%d." % i
@@ -155,7 +169,7 @@ def vit_forward(W, img, n_surgery=5):
         else:                                                        # :309-330
             src = x if x_ori is None else x_ori
             x_res, x_ori_res, p = _surgery_attention(
-                _layer_norm(src, W[o + "ln_1.weight"], W[o + "ln_1.bias"]), W, o, H)
+                _layer_norm(src, W[o + "ln_1.weight"], W[o + "ln_1.bias"]), W, o, H, ex_attn)
             mid = src + x_ori_res
             if i > first:
                 # aliasing quirk: all_feats[i-1] is a view of the previous x_ori, which the in-place
@@ -173,11 +187,28 @@ def vit_forward(W, img, n_surgery=5):
     return out, attns, feats
 
 
-def generate_clip_fts(W, img, n_surgery=5):
+def generate_clip_fts(W, img, n_surgery=5, ex_feats=None):
     """clip/clip.py:348-358: normalise over the TOKEN axis (dim=1), stack the lists."""
-    tok, attns, feats = vit_forward(W, img, n_surgery)
+    tok, attns, feats = vit_forward(W, img, n_surgery, ex_feats)
     tok = tok / tok.norm(dim=1, keepdim=True)
     return tok, torch.stack(attns, 0), torch.stack(feats, 0)
+
+
+# --------------------------------------------------------------------------- attribute bank (a10)
+
+
+def attrmap2clsmap(attri_flag, attr_maps):
+    """utils/attrutils.py:11-17: attr_maps [B,n_p,A] @ attri_flag[cls,A]^T."""
+    return attr_maps @ attri_flag.unsqueeze(0).permute(0, 2, 1)
+
+
+def attr2cls_embedings(text_features, text_attri, num_classes):
+    """utils/attrutils.py:19-29 with the foreground rows added at :25 (the reference adds ALL text rows there, which only
+    broadcasts when there are no background rows -- the two agree in that case; model/load_attr.py:112 is the live form)."""
+    fg, bg = text_features[:num_classes], text_features[num_classes:]
+    corr = (fg @ text_attri).softmax(dim=-1)
+    agg = torch.cat([corr @ text_attri.t() + fg, bg], dim=0)
+    return (agg / agg.norm(dim=1, keepdim=True)).permute(1, 0)
 
 
 # --------------------------------------------------------------------------- CAM (a9)

@@ -64,9 +64,9 @@ def load():
         import clip  # noqa
         import clip.clip_surgery_model as csm
         from utils import PAR as par_mod
-        from utils import affutils, camutils, evaluate
+        from utils import affutils, camutils, evaluate, attrutils
         from model import model_excel, load_attr
-    _loaded.update(clip=clip, csm=csm, PAR=par_mod.PAR, affutils=affutils, camutils=camutils,
+    _loaded.update(clip=clip, csm=csm, PAR=par_mod.PAR, affutils=affutils, camutils=camutils, attrutils=attrutils,
                    evaluate=evaluate, model_excel=model_excel, load_attr=load_attr)
     return types.SimpleNamespace(**_loaded)
 

@@ -1,0 +1,69 @@
+"""GPU parity: LVC branch of the encoder (Attention.forward with ex_feats,
+clip/clip_surgery_model.py:127-141) and utils/attrutils.py (a10), vs the reference's golden outputs and the oracle."""
+import pytest
+import torch
+
+from excel_b200 import synth
+from oracle import port
+from oracle.make_golden_cfg import TINY
+
+pytestmark = pytest.mark.gpu
+t = torch.from_numpy
+
+
+def test_lvc_attention_vs_oracle():
+    """ex_attn: rows are probability vectors over the kept (>= batch mean) neighbours; values match the oracle except where a
+    similarity sits within rounding of the batch mean (the reference's `< 0 -> -inf` cut is discontinuous there)."""
+    from excel_b200.encoder import lvc_attention
+    g = torch.Generator().manual_seed(5)
+    ex = torch.randn(3, 32, 14, 14, generator=g)
+    ex = ex + torch.nn.functional.avg_pool2d(torch.nn.functional.pad(ex, [2] * 4, mode="replicate"), 5, stride=1)
+    got = lvc_attention(ex.cuda()).cpu()
+    ref = port.lvc_attention(ex)
+    assert (got.sum(-1) - 1).abs().max() < 1e-5
+    q = torch.nn.functional.normalize(ex.flatten(2), dim=1)
+    sim = torch.einsum("bcm,bcn->bmn", q, q)
+    near_cut = ((sim - sim.mean()) * 3).abs() < 1e-5
+    rows_ok = ~near_cut.any(-1)
+    assert rows_ok.float().mean() > 0.99
+    assert (got - ref)[rows_ok].abs().max() < 1e-6
+
+
+def test_lvc_encoder_tiny_golden(golden):
+    from excel_b200.encoder import SurgeryViT, generate_clip_fts
+    G = golden("lvc")
+    enc = SurgeryViT(port.random_visual_weights(seed=3, **TINY))
+    imgs = synth.images(2, 96, seed=13).cuda()
+    tok, attn, feats = generate_clip_fts(imgs, enc, ex_feats=t(G["ex"]).cuda())
+    assert (tok.cpu() - t(G["tok"])).abs().max() < 2e-5
+    assert (attn.cpu() - t(G["attn"])).abs().max() < 2e-5
+    assert (feats.cpu() - t(G["feats"])).abs().amax(dim=(1, 2, 3)).max() < 2e-4
+    tok0, _, _ = generate_clip_fts(imgs, enc)
+    assert (tok0 - tok).abs().max() > 1e-3                         # the LVC bias is not a no-op
+
+
+def test_lvc_model_forward_b16_vs_oracle():
+    """ExCEL_model.forward(img, ex_feats) == clip_feature_surgery(generate_clip_fts(img, ex_feats)) (model_excel.py:50-53)."""
+    from excel_b200.encoder import SurgeryViT, generate_clip_fts
+    from excel_b200.clip import clip_feature_surgery
+    W = port.random_visual_weights(seed=1)
+    imgs = synth.images(2, 224, seed=21)
+    ex = torch.randn(2, 256, 14, 14, generator=torch.Generator().manual_seed(8))
+    text = synth.text_bank(45, 512, seed=3)
+    tok, attn, feats = generate_clip_fts(imgs.cuda(), SurgeryViT(W), ex_feats=ex.cuda())
+    attr = clip_feature_surgery(tok, text.cuda())[:, 1:, :20].cpu()
+    tok_r, attn_r, feats_r = port.generate_clip_fts(W, imgs, ex_feats=ex)
+    attr_r = port.clip_feature_surgery(tok_r, text)[:, 1:, :20]
+    assert (attn.cpu() - attn_r).abs().max() < 5e-5 and (tok.cpu() - tok_r).abs().max() < 1e-4
+    assert (attr - attr_r).abs().max() < 1e-3                      # north_star: fp32 CAM values within 1e-3
+
+
+def test_attrutils_vs_reference_golden(golden):
+    from excel_b200 import attrutils
+    G = golden("lvc")
+    clsmap = attrutils.attrmap2clsmap(t(G["flag"]).cuda(), t(G["amap"]).cuda())
+    assert clsmap.shape == (2, 36, 20) and (clsmap.cpu() - t(G["clsmap"])).abs().max() < 1e-5
+    agg = attrutils.attr2cls_embedings(t(G["tf"]).cuda(), t(G["bank"]).cuda(), 20)
+    assert agg.shape == (64, 20) and (agg.cpu() - t(G["agg"])).abs().max() < 1e-6
+    with pytest.raises(RuntimeError):
+        attrutils.attrmap2clsmap(t(G["flag"]), t(G["amap"]))          # CPU tensors: no fallback

@@ -88,3 +88,23 @@ def test_label_utils_golden(golden):
     v, l = port.lam_to_label(t(G["cam"]), t(G["cls"]), 0.45, 0.6, 0.3, True, 255)
     assert np.array_equal(l.numpy(), G["l_mid"]) and np.array_equal(v.numpy(), G["valid"])
     assert np.array_equal(port.lam_to_label(t(G["cam"]), t(G["cls"]), 0.45)[1].numpy(), G["l_bkg"])
+
+
+def test_lvc_branch_and_attrutils_oracle_vs_reference_golden(golden):
+    """oracle/port.py, LVC branch of the surgery attention (clip/clip_surgery_model.py:127-141) and utils/attrutils.py,
+    against outputs of the unmodified reference (oracle/make_golden_lvc.py)."""
+    import torch
+    from excel_b200 import synth
+    from oracle import port
+    from oracle.make_golden_cfg import TINY, checksum
+    G = golden("lvc")
+    t = torch.from_numpy
+    W = port.random_visual_weights(seed=3, **TINY)
+    imgs = synth.images(2, 96, seed=13)
+    assert abs(checksum(*[v for k, v in W.items() if k != "meta"]) - float(G["chk_w"])) < 1e-6 * float(G["chk_w"])
+    tok, attn, feats = port.generate_clip_fts(W, imgs, ex_feats=t(G["ex"]))
+    assert (tok - t(G["tok"])).abs().max() < 2e-5
+    assert (attn - t(G["attn"])).abs().max() < 2e-5
+    assert (feats - t(G["feats"])).abs().max() < 2e-4
+    assert (port.attrmap2clsmap(t(G["flag"]), t(G["amap"])) - t(G["clsmap"])).abs().max() < 1e-5
+    assert (port.attr2cls_embedings(t(G["tf"]), t(G["bank"]), 20) - t(G["agg"])).abs().max() < 1e-6
