@@ -32,6 +32,7 @@ SIGNATURES = {
     "excel_svc_cams_to_planes": ([_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p], _i),
     "excel_token_normalize": ([_p, _i, _i, _i, _p, _p, _p], _i),
     "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _p, _p], _i),
+    "excel_flip_merge": ([_p, _i, _i, _i, _i, _p, _p], _i),
     "excel_vit_workspace_bytes": ([_i, _i, _i, _i, _i], _i64),
     "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
     "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p], _i),

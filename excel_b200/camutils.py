@@ -13,11 +13,12 @@ def cure_attr_map(model, inputs, ex_feats):
 def merge_flipped_maps(attr_2b, b, gh, gw):
     """utils/camutils.py:19-26: element-max of the maps of x and flip(x) (un-flipped), per-(b,c) min subtracted,
     divided by (max + 1e-5).  attr_2b [2b, n_p, K] -> [b, n_p, K]."""
-    lam = attr_2b.permute(0, 2, 1).reshape(2 * b, -1, gh, gw)
-    lam = torch.max(lam[:b], lam[b:].flip(-1))
-    lam = lam - lam.amin(dim=(2, 3), keepdim=True)
-    lam = lam / (lam.amax(dim=(2, 3), keepdim=True) + 1e-5)
-    return lam.reshape(b, -1, gh * gw).permute(0, 2, 1)
+    x = _lib.f32c(attr_2b)
+    if x.shape[0] != 2 * b or x.shape[1] != gh * gw:
+        raise RuntimeError(f"merge_flipped_maps: expected [{2 * b}, {gh * gw}, K], got {tuple(x.shape)}")
+    out = torch.empty((b, gh * gw, x.shape[2]), dtype=torch.float32, device=x.device)
+    _lib.call("excel_flip_merge", _lib.ptr(x), b, gh, gw, x.shape[2], _lib.ptr(out), _lib.stream())
+    return out
 
 
 def cure_attr_map_flip(model, inputs, ex_fts=True, flip=True, raw_fts=None):

@@ -100,6 +100,40 @@ extern "C" int excel_token_normalize(const float* tok, int B, int N, int E, floa
     return check_launch("token_div_kernel");
 }
 
+// utils/camutils.py:19-26 (cure_attr_map_flip): out[b,p,k] = (m - min_p m) / (max_p (m - min_p m) + 1e-5),
+// m[b,p,k] = max(x[b,p,k], x[B+b, flip_x(p), k]); x [2B, gh*gw, K].  One block per (k, b).
+__global__ void __launch_bounds__(256)
+flip_merge_kernel(const float* __restrict__ x, int B, int gh, int gw, int K, float* __restrict__ out) {
+    __shared__ float red[32];
+    const int k = blockIdx.x, b = blockIdx.y, np = gh * gw;
+    const float* xa = x + (int64_t)b * np * K + k;
+    const float* xb = x + (int64_t)(B + b) * np * K + k;
+    float mn = INFINITY;
+    for (int p = threadIdx.x; p < np; p += 256) {
+        const int py = p / gw, px = p - py * gw;
+        mn = fminf(mn, fmaxf(xa[(int64_t)p * K], xb[(int64_t)(py * gw + gw - 1 - px) * K]));
+    }
+    mn = block_reduce(mn, red, OpMin(), INFINITY);
+    float mx = -INFINITY;
+    for (int p = threadIdx.x; p < np; p += 256) {
+        const int py = p / gw, px = p - py * gw;
+        mx = fmaxf(mx, fmaxf(xa[(int64_t)p * K], xb[(int64_t)(py * gw + gw - 1 - px) * K]) - mn);
+    }
+    mx = block_reduce(mx, red, OpMax(), -INFINITY);
+    const float den = mx + 1e-5f;
+    for (int p = threadIdx.x; p < np; p += 256) {
+        const int py = p / gw, px = p - py * gw;
+        out[((int64_t)b * np + p) * K + k] = (fmaxf(xa[(int64_t)p * K], xb[(int64_t)(py * gw + gw - 1 - px) * K]) - mn) / den;
+    }
+}
+
+extern "C" int excel_flip_merge(const float* attr_2b, int B, int gh, int gw, int K, float* out, void* stream) {
+    XL_REQUIRE(B >= 0 && gh >= 1 && gw >= 1 && K >= 1 && B <= 65535, "flip_merge: bad shape");
+    if (B == 0) return 0;
+    flip_merge_kernel<<<dim3(K, B), 256, 0, (cudaStream_t)stream>>>(attr_2b, B, gh, gw, K, out);
+    return check_launch("flip_merge_kernel");
+}
+
 extern "C" int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, float* S_ws,
                                  float* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

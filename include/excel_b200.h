@@ -108,6 +108,10 @@ int excel_token_normalize(const float* tok, int B, int N, int E, float* norm_ws,
 int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, float* S_ws, float* out,
                       void* stream);
 
+/* utils/camutils.py:19-26 (cure_attr_map_flip): attr_2b [2B, gh*gw, K] = maps of [x, flip(x)] -> out [B, gh*gw, K]:
+ * element-max of the un-flipped pair, minus its per-(b,k) spatial min, divided by (max + 1e-5). */
+int excel_flip_merge(const float* attr_2b, int B, int gh, int gw, int K, float* out, void* stream);
+
 /* ---------------------------------------------------------------- ViT (clip/clip_surgery_model.py) */
 
 /* Weights of one ResidualAttentionBlock (clip/clip_surgery_model.py:285-337); all device pointers, fp32,

@@ -67,3 +67,20 @@ def test_attrutils_vs_reference_golden(golden):
     assert agg.shape == (64, 20) and (agg.cpu() - t(G["agg"])).abs().max() < 1e-6
     with pytest.raises(RuntimeError):
         attrutils.attrmap2clsmap(t(G["flag"]), t(G["amap"]))          # CPU tensors: no fallback
+
+
+def test_flip_merge_vs_reference_golden_and_oracle(golden):
+    """utils/camutils.py:19-26 (cure_attr_map_flip post-processing) as one kernel."""
+    from excel_b200.camutils import merge_flipped_maps
+    G = golden("cam")
+    lam2b = t(G["lam2b"])
+    b = lam2b.shape[0] // 2
+    g = int(round(lam2b.shape[1] ** 0.5))
+    got = merge_flipped_maps(lam2b.cuda(), b, g, g).cpu()
+    assert (got - t(G["merged"])).abs().max() < 1e-6
+    x = torch.rand(6, 7 * 9, 20, generator=torch.Generator().manual_seed(0))          # non-square grid
+    lam = x.permute(0, 2, 1).reshape(6, 20, 7, 9)
+    lam = torch.max(lam[:3], lam[3:].flip(-1))
+    lam = lam - lam.amin(dim=(2, 3), keepdim=True)
+    lam = (lam / (lam.amax(dim=(2, 3), keepdim=True) + 1e-5)).reshape(3, 20, 63).permute(0, 2, 1)
+    assert (merge_flipped_maps(x.cuda(), 3, 7, 9).cpu() - lam).abs().max() < 1e-6

@@ -124,7 +124,8 @@ def test_install_rebinds_reference_symbols():
     assert importlib.import_module("utils.PAR").PAR is not par.PAR
 
 
-def test_merge_flipped_maps_matches_oracle():
+def test_merge_flipped_maps_has_no_cpu_path():
+    import pytest
     from excel_b200.camutils import merge_flipped_maps
-    x = torch.rand(4, 36, 20, generator=torch.Generator().manual_seed(0))
-    assert torch.allclose(merge_flipped_maps(x, 2, 6, 6), port.cure_attr_map_flip_post(x, 6), atol=1e-7)
+    with pytest.raises(RuntimeError):
+        merge_flipped_maps(torch.rand(4, 36, 20), 2, 6, 6)
