@@ -23,7 +23,8 @@
 namespace xl {
 
 constexpr int kABK = 64;                                  // head dim == one 64-wide k block
-constexpr int kAStages = 3;                               // operand ring: 192 KB in flight per SM
+constexpr int kAStages = 3;                               // MODE 1 operand ring (X and Y tiles per stage): 192 KB in flight per SM
+constexpr int kAYStages = 4;                              // MODE 0: Y-only ring (32 KB stages) beside a double-buffered X tile
 constexpr int kAAcc = 4;                                  // TMEM accumulators (4 x 128 columns)
 constexpr uint32_t kATile = 128 * kABK * 2;               // 16 KB: one 128-row fp16 operand tile
 constexpr uint32_t kAStage = 4 * kATile;                  // X_hi, X_lo, Y_hi, Y_lo
@@ -45,10 +46,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* ebuf = tiles + kAStages * kAStage;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ebuf + kAEpi);
-    uint64_t* empty_bar = full_bar + kAStages;
-    uint64_t* acc_full = empty_bar + kAStages;
+    uint64_t* empty_bar = full_bar + kAYStages;
+    uint64_t* acc_full = empty_bar + kAYStages;
     uint64_t* acc_empty = acc_full + kAAcc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAAcc);
+    uint64_t* x_full = acc_empty + kAAcc;                 // [2] MODE 0: the item's X tile (shared by all its key blocks)
+    uint64_t* x_empty = x_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + 2);
+    // MODE 0 shared-memory plan: X double buffer (2 x 32 KB: hi | lo), then kAYStages Y stages (32 KB: hi | lo).  An SM ingests
+    // ~64 B/clk from L2; not re-fetching X for each of the item's key blocks halves the bytes per S tile.
+    uint8_t* xbuf = tiles;
+    uint8_t* yring = tiles + 2 * 2 * kATile;
+    constexpr int NST = MODE == 0 ? kAYStages : kAStages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.N + 127) / 128;                   // row blocks == key blocks
@@ -57,9 +65,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int items = MODE == 0 ? p.B * TH * nblk : p.B * nblk * nblk;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kAStages; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&x_full[s], 1);
+            mbar_init(&x_empty[s], 1);
         }
         for (int s = 0; s < kAAcc; ++s) {
             mbar_init(&acc_full[s], 1);
@@ -86,42 +98,64 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // whole warp runs the control flow, one elected lane issues (keeps the TMA / tcgen05 operands on the uniform datapath)
         const bool leader = elect_one_sync();
         if (leader) tma_prefetch_desc(&tmQ);
-        int it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x)
+        int it = 0, ni = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++ni)
             for (int j = 0; j < inner; ++j, ++it) {
                 int b, h, rb, kb;
                 decode(item, j, b, h, rb, kb);
-                const int s = it % kAStages;
-                mbar_wait(&empty_bar[s], ((it / kAStages) & 1) ^ 1);
-                uint8_t* st = tiles + s * kAStage;
                 const int xr = b * p.N + rb * 128, yr = b * p.N + kb * 128;
                 const int ty = h / p.H, hd = h - ty * p.H;
                 const int xc = p.xo[ty] + hd * kABK, yc = p.yo[ty] + hd * kABK;
-                if (leader) {
-                    mbar_arrive_expect_tx(&full_bar[s], kAStage);
-                    tma_load_2d(st, &tmQ, &full_bar[s], xc, xr);
-                    tma_load_2d(st + kATile, &tmQ, &full_bar[s], xc + p.lo_off, xr);
-                    tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], yc, yr);
-                    tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], yc + p.lo_off, yr);
+                if (MODE == 0) {
+                    if (j == 0) {   // the item's X tile, once
+                        const int xs = ni & 1;
+                        mbar_wait(&x_empty[xs], ((ni >> 1) & 1) ^ 1);
+                        if (leader) {
+                            mbar_arrive_expect_tx(&x_full[xs], 2 * kATile);
+                            tma_load_2d(xbuf + xs * 2 * kATile, &tmQ, &x_full[xs], xc, xr);
+                            tma_load_2d(xbuf + xs * 2 * kATile + kATile, &tmQ, &x_full[xs], xc + p.lo_off, xr);
+                        }
+                    }
+                    const int s = it % kAYStages;
+                    mbar_wait(&empty_bar[s], ((it / kAYStages) & 1) ^ 1);
+                    uint8_t* st = yring + s * 2 * kATile;
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[s], 2 * kATile);
+                        tma_load_2d(st, &tmQ, &full_bar[s], yc, yr);
+                        tma_load_2d(st + kATile, &tmQ, &full_bar[s], yc + p.lo_off, yr);
+                    }
+                } else {
+                    const int s = it % kAStages;
+                    mbar_wait(&empty_bar[s], ((it / kAStages) & 1) ^ 1);
+                    uint8_t* st = tiles + s * kAStage;
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[s], kAStage);
+                        tma_load_2d(st, &tmQ, &full_bar[s], xc, xr);
+                        tma_load_2d(st + kATile, &tmQ, &full_bar[s], xc + p.lo_off, xr);
+                        tma_load_2d(st + 2 * kATile, &tmQ, &full_bar[s], yc, yr);
+                        tma_load_2d(st + 3 * kATile, &tmQ, &full_bar[s], yc + p.lo_off, yr);
+                    }
                 }
             }
     } else if (warp == 1) {
         const bool leader = elect_one_sync();
         const uint32_t tiles0 = smem_u32(tiles);
-        int it = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x)
+        int it = 0, ni = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++ni)
             for (int j = 0; j < inner; ++j, ++it) {
                 int b, h, rb, kb;
                 decode(item, j, b, h, rb, kb);
-                const int buf = it % kAAcc, s = it % kAStages;
+                const int buf = it % kAAcc, s = it % NST;
                 mbar_wait(&acc_empty[buf], ((it / kAAcc) & 1) ^ 1);
-                mbar_wait(&full_bar[s], (it / kAStages) & 1);
+                if (MODE == 0 && j == 0) mbar_wait(&x_full[ni & 1], (ni >> 1) & 1);
+                mbar_wait(&full_bar[s], (it / NST) & 1);
                 tc_fence_after();
                 const uint32_t idesc = make_idesc((min(128, p.N - kb * 128) + 15) & ~15);   // padding keys are not computed
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * 128);
-                const uint32_t st = tiles0 + s * kAStage;
-                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kATile);
-                const uint64_t b_hi = umma_desc_sw128(st + 2 * kATile), b_lo = umma_desc_sw128(st + 3 * kATile);
+                const uint32_t xa = MODE == 0 ? tiles0 + (ni & 1) * 2 * kATile : tiles0 + s * kAStage;
+                const uint32_t yb = MODE == 0 ? tiles0 + 4 * kATile + s * 2 * kATile : tiles0 + s * kAStage + 2 * kATile;
+                const uint64_t a_hi = umma_desc_sw128(xa), a_lo = umma_desc_sw128(xa + kATile);
+                const uint64_t b_hi = umma_desc_sw128(yb), b_lo = umma_desc_sw128(yb + kATile);
                 if (leader) {
 #pragma unroll
                     for (int k = 0; k < kABK / 16; ++k) {
@@ -131,6 +165,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         umma_f16(tacc, a_hi + adv, b_hi + adv, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);
+                    if (MODE == 0 && j == inner - 1) umma_commit(&x_empty[ni & 1]);   // the item's X tile may be replaced
                     umma_commit(&acc_full[buf]);
                 }
             }
