@@ -86,12 +86,18 @@ __device__ __forceinline__ void stage_tile_async(float* sm, const float* __restr
 //           sum / sum-of-squares form is well conditioned;
 //   pass 2: a_k = -mean_c[(|I_k - I_0| / (std_c + 1e-8) / w1)^2] kept in registers, softmax over k,
 //           + w2 * (constant positional softmax), streamed out with evict-first stores.
-template <int NDIL>
+// STD: the reference's dilation set (1, 2, 4, 8, 12, 24; scripts/train_voc.py:112, tools/infer_lam.py:168) is baked in, so
+// that every neighbour address is an immediate offset of one base register -- the generic form spends a quarter of its
+// issue slots on address arithmetic (ncu: the kernel is issue-bound, not LDS- or HBM-bound).
+__device__ constexpr int kStdDil[6] = {1, 2, 4, 8, 12, 24};
+
+template <int NDIL, bool STD>
 __global__ void __launch_bounds__(256, 2)
 par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, float* __restrict__ aff,
-                    int H, int W, int Wp, int halo, ParGeom g, float w1) {
+                    int H, int W, int Wp, int halo_rt, ParGeom g, float w1) {
     constexpr int K = 8 * NDIL;
     extern __shared__ float sm[];
+    const int halo = STD ? 24 : halo_rt;
     const int TW = kTX + 2 * halo, TH = kTY + 2 * halo;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = blockIdx.z;
     stage_tile_async(sm, img + (int64_t)b * sb, sc, sy, 3, x0, y0, halo, TW, TH, H, W, threadIdx.y * 32 + threadIdx.x);
@@ -112,7 +118,7 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
 #pragma unroll
         for (int di = 0; di < NDIL; ++di) {
-            const int d = g.dil[di], dW = d * TW;
+            const int d = STD ? kStdDil[di] : g.dil[di], dW = d * TW;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
@@ -129,12 +135,14 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
         float amax = -INFINITY;
 #pragma unroll
         for (int di = 0; di < NDIL; ++di) {
-            const int d = g.dil[di], dW = d * TW;
+            const int d = STD ? kStdDil[di] : g.dil[di], dW = d * TW;
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
                 const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
-                const float t0 = fabsf(p[0] - c0) * r0, t1 = fabsf(p[cs] - c1) * r1, t2 = fabsf(p[2 * cs] - c2) * r2;
-                const float v = -(t0 * t0 + t1 * t1 + t2 * t2) / 3.f * 1.4426950408889634f;  // log2(e): exp2 below
+                const float t0 = (p[0] - c0) * r0, t1 = (p[cs] - c1) * r1, t2 = (p[2 * cs] - c2) * r2;
+                // -mean_c(t^2) * log2(e) (exp2 below); the channel mean as a multiplication: a true division costs a
+                // ~10-instruction slow-path check 48 times per pixel for at most 1 ulp of the exponent
+                const float v = (t0 * t0 + t1 * t1 + t2 * t2) * (-1.4426950408889634f / 3.f);
                 a[di * 8 + t] = v;
                 amax = fmaxf(amax, v);
             }
@@ -283,11 +291,14 @@ __device__ __forceinline__ void fix_border(float* sm, int np, int xl, int yl, in
 }
 
 // TY = tile height; NST = ring depth; KG = taps per ring stage.
-template <int CCH, int TY, int NST, int KG>
+// STD: the reference's dilation set baked in (see par_affinity_kernel): neighbour addresses become immediate offsets and the
+// six dilation rounds unroll.
+template <int CCH, int TY, int NST, int KG, bool STD>
 __global__ void __launch_bounds__(8 * TY + 32, 1)
 par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_constant__ CUtensorMap tm_in, int tma_in,
                    const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ plane_off, int img0,
-                   int H, int W, int halo, ParGeom g) {
+                   int H, int W, int halo_rt, ParGeom g) {
+    const int halo = STD ? 24 : halo_rt;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], tile_full, tile_empty;
     constexpr int NC = 8 * TY, NW = TY / 4;  // consumer threads / warps
@@ -362,9 +373,7 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
-#pragma unroll 1
-        for (int di = 0; di < g.n_dil; ++di) {
-            const int d = g.dil[di];
+        auto round = [&](int d) {   // the 8 taps of one dilation, KG per ring stage
             const int d4 = d * 4, dW4 = d * TW * 4;
             const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
 #pragma unroll
@@ -377,6 +386,13 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
                 if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with stage s
                 ++it;
             }
+        };
+        if constexpr (STD) {
+#pragma unroll
+            for (int di = 0; di < 6; ++di) round(kStdDil[di]);
+        } else {
+#pragma unroll 1
+            for (int di = 0; di < g.n_dil; ++di) round(g.dil[di]);
         }
         if (tma_in && pass + 1 < npass) {  // hand the mask tile back to the producer
             if (border) fence_proxy_async_smem();
@@ -466,14 +482,28 @@ static int set_smem(Kern kern, size_t bytes, const char* what) {
     return 0;
 }
 
+static bool is_std_dilations(const ParGeom& g) {
+    if (g.n_dil != 6) return false;
+    for (int i = 0; i < 6; ++i)
+        if (g.dil[i] != kStdDil[i]) return false;
+    return true;
+}
+
 template <int NDIL>
 static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy, float* aff, int B, int H, int W,
                            int Wp, const ParGeom& g, float w1, cudaStream_t st) {
     const int halo = max_dilation(g);
     const size_t smem = tile_smem_bytes(halo, 3);
-    if (int e = set_smem(par_affinity_kernel<NDIL>, smem, "par_affinity")) return e;
     dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), B), block(32, 8);
-    par_affinity_kernel<NDIL><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
+    if constexpr (NDIL == 6) {
+        if (is_std_dilations(g)) {
+            if (int e = set_smem(par_affinity_kernel<6, true>, smem, "par_affinity")) return e;
+            par_affinity_kernel<6, true><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
+            return check_launch("par_affinity_kernel<std>");
+        }
+    }
+    if (int e = set_smem(par_affinity_kernel<NDIL, false>, smem, "par_affinity")) return e;
+    par_affinity_kernel<NDIL, false><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
     return check_launch("par_affinity_kernel");
 }
 
@@ -492,10 +522,16 @@ static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, con
     constexpr int TY = par_ty(CCH), NST = par_nst(CCH), KG = par_kg(CCH);
     const int halo = max_dilation(g);
     const size_t smem = (size_t)(kTX + 2 * halo) * (TY + 2 * halo) * CCH * sizeof(float) + NST * KG * TY * kTX * sizeof(float) + 128;
-    if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG>, smem, "par_iterate")) return e;
     dim3 grid(ceil_div(W, kTX), ceil_div(H, TY), nimg);
-    par_iterate_kernel<CCH, TY, NST, KG><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
-                                                                      plane_off, img0, H, W, halo, g);
+    if (is_std_dilations(g)) {
+        if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG, true>, smem, "par_iterate")) return e;
+        par_iterate_kernel<CCH, TY, NST, KG, true><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in,
+                                                                                  out, plane_off, img0, H, W, halo, g);
+        return check_launch("par_iterate_kernel<std>");
+    }
+    if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG, false>, smem, "par_iterate")) return e;
+    par_iterate_kernel<CCH, TY, NST, KG, false><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
+                                                                             plane_off, img0, H, W, halo, g);
     return check_launch("par_iterate_kernel");
 }
 
