@@ -165,7 +165,7 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
 // Algorithmic bytes per pixel and step: 4*(K + 2*C); the K affinity planes are the stream.
 //
 //  * The affinity tile [K][64][32] is streamed by TMA (cp.async.bulk.tensor.3d) through a shared-memory ring of
-//    one-tap stages (8 KB), completion on mbarriers: the loads are asynchronous, cost no registers or LSU issue
+//    two-tap stages (16 KB), completion on mbarriers: the loads are asynchronous, cost no registers or LSU issue
 //    slots, and keep 56-120 KB in flight per SM (HBM needs ~45 KB per microsecond of latency and SM).
 //    The affinity workspace is internal, so its row pitch is padded to 4 floats (TMA stride rule) and
 //    out-of-image elements are zero-filled by the TMA unit.
@@ -174,7 +174,7 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
 //    compile-time-shifted LDS.128/LDS.64/LDS.32 combination for dilations 1 and 2.
 //  * CCH mask planes (+ halo, replicate padding applied at load) are staged in shared memory; images
 //    with more planes loop (the affinity re-read then comes from L2).
-// Ring geometry (par_ty / par_nst / par_kg below): 8 KB TMA stages; NST-1 of them in flight per CTA.
+// Ring geometry (par_ty / par_nst / par_kg below): 16 KB TMA stages; NST-1 of them in flight per CTA.
 
 // shared-memory loads on 32-bit shared addresses (keeps the address arithmetic 32-bit; `volatile` pins
 // them behind the mbarrier waits)
@@ -511,10 +511,10 @@ static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy,
 // Tile geometry: 32 x 64 pixel tiles, one CTA (16 consumer warps + the producer warp) per SM.  Against 32 x 32 tiles at two
 // CTAs per SM the halo shrinks from 5.25x to 3.4x the tile and a 4-plane pass keeps 16 warps per SM instead of 8 (measured at
 // 512^2 x 16, 20 steps: 3.87 -> 3.71 ms at 2 planes, 4.47 -> 4.39 ms at 3, 6.79 -> 5.52 ms at 4).  The affinity ring holds
-// 8 KB stages (one tap of the tile), as many as fit beside the mask planes.
+// 16 KB stages (two taps of the tile), as many as fit beside the mask planes.
 __host__ __device__ constexpr int par_ty(int) { return 64; }
-__host__ __device__ constexpr int par_nst(int cch) { return cch <= 2 ? 16 : (cch == 3 ? 12 : 8); }   // ring depth
-__host__ __device__ constexpr int par_kg(int) { return 1; }                                       // taps per stage
+__host__ __device__ constexpr int par_nst(int cch) { return cch <= 2 ? 8 : (cch == 3 ? 6 : 4); }   // ring depth
+__host__ __device__ constexpr int par_kg(int) { return 2; }                                     // taps per stage
 
 template <int CCH>
 static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, const float* in, float* out,
