@@ -37,6 +37,7 @@ SIGNATURES = {
     "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
     "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p], _i),
     "excel_lvc_attention": ([_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p], _i),
+    "excel_attn_pred": ([_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p], _i),
     "excel_row_softmax": ([_p, _i, _i, _p, _p], _i),
     "excel_row_l2_normalize": ([_p, _i, _i, _p, _p], _i),
     "excel_gemm_tc": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _p], _i),

@@ -77,6 +77,7 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
             float v = alpha * acc[i][j];
             if (bias) v += bias[gn];
             if (act == 1) v = v * (1.f / (1.f + expf(-1.702f * v)));  // QuickGELU x*sigmoid(1.702x)
+            else if (act == 2) v = fmaxf(v, 0.f);                       // ReLU
             if (residual) v += residual[(int64_t)gm * ldc + gn];
             C[(int64_t)gm * ldc + gn] = v;
         }

@@ -236,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
                         // QuickGELU x * sigmoid(1.702 x) (clip_surgery_model.py:280-282), exp2 domain
                         if (act == 1) x = __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x));
+                        else if (act == 2) x = fmaxf(x, 0.f);   // ReLU (model/segformer_head.py:24)
                         v[j] = x;
                     }
                     if (p.C) {
@@ -312,6 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float x = alpha * __uint_as_float(r[j + e]);
                         if (bias && nb + j + e < p.N) x += __ldg(bias + nb + j + e);
                         if (act == 1) x = __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x));  // QuickGELU
+                        else if (act == 2) x = fmaxf(x, 0.f);
                         v[e] = x;
                     }
                     *reinterpret_cast<float4*>(stage + trow * kPitch + j) = make_float4(v[0], v[1], v[2], v[3]);

@@ -94,9 +94,44 @@ row_l2_normalize_kernel(const float* __restrict__ x, int64_t rows, int cols, flo
     for (int j = lane; j < cols; j += 32) out[row * cols + j] = x[row * cols + j] / n;
 }
 
+// x <- sigmoid((x - mean * beta) * gamma), elementwise (model/model_excel.py:75-76)
+__global__ void centred_sigmoid_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ mean, float beta, float gamma) {
+    const float sub = mean[0] * beta;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = 1.f / (1.f + expf(-(x[i] - sub) * gamma));
+}
+
+// normalise + similarity + batch mean, shared by the LVC bias and attn_pred: sim [B,np,np] and mean_ws[0]
+static int cosine_similarity_and_mean(const float* feats, int B, int C, int np, float* qt_ws, double* rowsum_ws, float* mean_ws,
+                                      float* sim, cudaStream_t st) {
+    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 128), B), 128, 0, st>>>(feats, C, np, qt_ws);
+    if (int e = check_launch("lvc_normalize_t_kernel")) return e;
+    // sim[b] = qt[b] qt[b]^T  (exact fp32)
+    if (int e = sgemm2(qt_ws, qt_ws, sim, nullptr, nullptr, np, np, C, C, C, np, B, (int64_t)np * C, (int64_t)np * C,
+                       (int64_t)np * np, 1, 0, 0, 0, 1.f, 1, 0, st)) return e;
+    const int64_t rows = (int64_t)B * np;
+    row_sum_f64_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(sim, rows, np, rowsum_ws);
+    if (int e = check_launch("row_sum_f64_kernel")) return e;
+    total_mean_kernel<<<1, 1024, 0, st>>>(rowsum_ws, rows, (double)rows * np, mean_ws);
+    return check_launch("total_mean_kernel");
+}
+
 }  // namespace xl
 
 using namespace xl;
+
+extern "C" int excel_attn_pred(const float* feats, int B, int C, int np, float beta, float gamma, float* qt_ws,
+                               double* rowsum_ws, float* mean_ws, float* attn_pred, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    XL_REQUIRE(B >= 0 && C >= 1 && np >= 1 && B <= 65535, "attn_pred: bad shape B=%d C=%d np=%d", B, C, np);
+    XL_REQUIRE(feats && qt_ws && rowsum_ws && mean_ws && attn_pred, "attn_pred: missing buffers");
+    if (B == 0) return 0;
+    if (int e = cosine_similarity_and_mean(feats, B, C, np, qt_ws, rowsum_ws, mean_ws, attn_pred, st)) return e;
+    const int64_t n = (int64_t)B * np * np;
+    centred_sigmoid_kernel<<<(unsigned)(ceil_div64(n, 256) < 148 * 16 ? ceil_div64(n, 256) : 148 * 16), 256, 0, st>>>(attn_pred, n, mean_ws,
+                                                                                                              beta, gamma);
+    return check_launch("centred_sigmoid_kernel");
+}
 
 extern "C" int excel_row_softmax(const float* x, int rows, int cols, float* out, void* stream) {
     XL_REQUIRE(rows >= 0 && cols >= 1, "row_softmax: bad shape");
@@ -118,16 +153,9 @@ extern "C" int excel_lvc_attention(const float* ex_feats, int B, int C, int np, 
     XL_REQUIRE(B >= 0 && C >= 1 && np >= 1 && B <= 65535, "lvc_attention: bad shape B=%d C=%d np=%d", B, C, np);
     XL_REQUIRE(ex_feats && qt_ws && rowsum_ws && mean_ws && ex_attn, "lvc_attention: missing buffers");
     if (B == 0) return 0;
-    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 128), B), 128, 0, st>>>(ex_feats, C, np, qt_ws);
-    if (int e = check_launch("lvc_normalize_t_kernel")) return e;
-    // sim[b] = qt[b] qt[b]^T  (exact fp32), written into ex_attn and transformed in place row by row
-    if (int e = sgemm2(qt_ws, qt_ws, ex_attn, nullptr, nullptr, np, np, C, C, C, np, B, (int64_t)np * C, (int64_t)np * C,
-                       (int64_t)np * np, 1, 0, 0, 0, 1.f, 1, 0, st)) return e;
+    // sim[b] = cosine similarity, written into ex_attn and transformed in place row by row
+    if (int e = cosine_similarity_and_mean(ex_feats, B, C, np, qt_ws, rowsum_ws, mean_ws, ex_attn, st)) return e;
     const int64_t rows = (int64_t)B * np;
-    row_sum_f64_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(ex_attn, rows, np, rowsum_ws);
-    if (int e = check_launch("row_sum_f64_kernel")) return e;
-    total_mean_kernel<<<1, 1024, 0, st>>>(rowsum_ws, rows, (double)rows * np, mean_ws);
-    if (int e = check_launch("total_mean_kernel")) return e;
     row_softmax_kernel<true><<<(unsigned)ceil_div64(rows, 8), 256, 0, st>>>(ex_attn, rows, np, mean_ws, beta, gamma, ex_attn);
     return check_launch("row_softmax_kernel<masked>");
 }

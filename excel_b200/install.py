@@ -40,13 +40,43 @@ def install(reference_root=None):
 
     patch("utils.attrutils", "attrmap2clsmap", my_attr.attrmap2clsmap)
     patch("utils.attrutils", "attr2cls_embedings", my_attr.attr2cls_embedings)
+    # decoder-side inference: only without autograd and in eval mode (Dropout2d, trainable decoder)
+    import torch
+    from . import decoder as my_dec
+    ref_model = importlib.import_module("model.model_excel")
+    ref_head = importlib.import_module("model.segformer_head")
+    orig_forward, orig_head_forward = ref_model.ExCEL_model.forward, ref_head.SegFormerHead.forward
+
+    def model_forward(self, img, ex_feats=None):
+        if torch.is_grad_enabled() or self.training or not img.is_cuda:
+            return orig_forward(self, img, ex_feats)
+        return my_dec.excel_model_forward(self, img, ex_feats)
+
+    def head_forward(self, x_all):
+        if torch.is_grad_enabled() or self.training or not x_all.is_cuda:
+            return orig_head_forward(self, x_all)
+        return my_dec.segformer_head(self, x_all)
+
+    originals["model.model_excel.ExCEL_model.forward"] = None   # class attributes: restored explicitly by uninstall()
+    _CLASS_PATCHES[:] = [(ref_model.ExCEL_model, "forward", orig_forward), (ref_head.SegFormerHead, "forward", orig_head_forward)]
+    ref_model.ExCEL_model.forward = model_forward
+    ref_head.SegFormerHead.forward = head_forward
+
     for mod in ("clip", "clip.clip"):
         patch(mod, "generate_clip_fts", my_enc.generate_clip_fts)
         patch(mod, "clip_feature_surgery", my_clip.clip_feature_surgery)
     return originals
 
 
+_CLASS_PATCHES = []
+
+
 def uninstall(originals):
+    for cls, attr, obj in _CLASS_PATCHES:
+        setattr(cls, attr, obj)
+    _CLASS_PATCHES.clear()
     for name, obj in originals.items():
+        if obj is None:
+            continue
         module_name, attr = name.rsplit(".", 1)
         setattr(importlib.import_module(module_name), attr, obj)

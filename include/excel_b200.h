@@ -155,6 +155,11 @@ int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_st
 int excel_lvc_attention(const float* ex_feats, int B, int C, int np, float beta, float gamma, float* qt_ws,
                         double* rowsum_ws, float* mean_ws, float* ex_attn, void* stream);
 
+/* model/model_excel.py:71-76 (attn_pred): feats [B,C,np] -> sigmoid((cosine similarity - batch mean * beta) * gamma)
+ * [B,np,np]; same workspaces as excel_lvc_attention. */
+int excel_attn_pred(const float* feats, int B, int C, int np, float beta, float gamma, float* qt_ws, double* rowsum_ws,
+                    float* mean_ws, float* attn_pred, void* stream);
+
 /* utils/attrutils.py helpers: out[r,:] = softmax(x[r,:]) / x[r,:] / ||x[r,:]||_2 for x [rows, cols]. */
 int excel_row_softmax(const float* x, int rows, int cols, float* out, void* stream);
 int excel_row_l2_normalize(const float* x, int rows, int cols, float* out, void* stream);
@@ -187,7 +192,7 @@ int excel_lam_to_label(const float* cam, const float* cls_label, int B, int C, i
 
 /* C[b] = act(alpha * A[b] * op(B[b]) + bias) + residual[b]; exact fp32 (SIMT).  A [M,K] (lda); B [N,K] (ldb)
  * if b_is_nk (nn.Linear weight layout) else [K,N]; C, residual [M,N] (ldc); act: 0 none, 1 QuickGELU
- * (clip/clip_surgery_model.py:280-282). */
+ * (clip/clip_surgery_model.py:280-282), 2 ReLU. */
 int excel_sgemm(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
                 int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t strideA, int64_t strideB, int64_t strideC,
                 float alpha, int b_is_nk, int act, void* stream);

@@ -64,6 +64,13 @@ def main():
     gate("LVC: generate_clip_fts.all_feats", (feats_l - feats_lr).abs().max().item(), 2e-4)
     print(f"       LVC bias changes attr_maps_raw by up to {(attr_lvc_ref - attr_ref).abs().max().item():.3e}")
 
+    # ---- decoder-side inference (f4): SegFormerHead + attn_pred on the reference's own all_feats
+    Wd = {k: v.detach() for k, v in model.decoder_fts_fuse.state_dict().items()}
+    g_ = args.size // 16
+    x_all = feats_ref[:, :, 1:].permute(0, 1, 3, 2).reshape(feats_ref.shape[0], args.batch, feats_ref.shape[-1], g_, g_)
+    gate("SegFormerHead.forward (attn_fts)", (port.segformer_head(Wd, x_all) - attn_fts).abs().max().item(), 1e-5)
+    gate("attn_pred", (port.attn_pred(attn_fts) - attn_pred).abs().max().item(), 1e-6)
+
     # ---- attrutils (a10): no live caller in the reference, checked function by function
     gA = torch.Generator().manual_seed(9)
     flag = (torch.rand(20, 112, generator=gA) > 0.8).float()

@@ -42,6 +42,19 @@ def main():
     clsmap = ref.attrutils.attrmap2clsmap(flag, amap)
     tf, bank = torch.randn(20, 64, generator=g), torch.randn(64, 112, generator=g)
     agg = ref.attrutils.attr2cls_embedings(tf, bank, 20)
+    # decoder-side inference (f4): the reference's SegFormerHead (seeded) on the tiny model's all_feats, and attn_pred
+    import importlib
+    seg_mod = importlib.import_module("model.segformer_head")
+    torch.manual_seed(123)
+    head = seg_mod.SegFormerHead(in_channels=TINY["width"], embedding_dim=32, num_classes=21, index=TINY["layers"]).eval()
+    x_all = feats[:, :, 1:].permute(0, 1, 3, 2).reshape(TINY["layers"], 2, TINY["width"], 6, 6)
+    fts = head(x_all)
+    af = torch.nn.functional.normalize(fts.reshape(2, 32, 36), dim=1)
+    apred = af.transpose(2, 1).bmm(af)
+    apred = torch.sigmoid((apred - torch.mean(apred) * 1.) * 3.0)                 # model/model_excel.py:71-76
+    head_sd = {"head." + k: v.numpy() for k, v in head.state_dict().items()}
+    np.savez(os.path.join(OUT, "decoder.npz"), fts=fts.numpy(), attn_pred=apred.numpy(), **head_sd)
+    print("decoder.npz", os.path.getsize(os.path.join(OUT, "decoder.npz")) // 1024, "KiB")
     np.savez(os.path.join(OUT, "lvc.npz"), ex=ex.numpy(), tok=tok.numpy(), attn=attn.numpy(), feats=feats.numpy(),
              ex_attn=port.lvc_attention(ex).numpy(), chk_w=checksum(*[v for k, v in W.items() if k != "meta"]), chk_img=checksum(imgs),
              flag=flag.numpy(), amap=amap.numpy(), clsmap=clsmap.numpy(), tf=tf.numpy(), bank=bank.numpy(), agg=agg.numpy())

@@ -194,6 +194,29 @@ def generate_clip_fts(W, img, n_surgery=5, ex_feats=None):
     return tok, torch.stack(attns, 0), torch.stack(feats, 0)
 
 
+# --------------------------------------------------------------------------- decoder-side inference (f4)
+
+
+def segformer_head(Wd, x_all):
+    """SegFormerHead.forward at inference (model/segformer_head.py:66-77).  Wd: state_dict-style weights
+    (linears_modulelist.{l}.proj / proj_2, linear_fuse); x_all [L,B,C,h,w] -> [B,E,h,w]."""
+    L, B, C, h, w = x_all.shape
+    outs = []
+    for l in range(L):
+        x = x_all[l].float().flatten(2).transpose(1, 2)                                                # :22
+        x = F.relu(F.linear(x, Wd["linears_modulelist.%d.proj.weight" % l], Wd["linears_modulelist.%d.proj.bias" % l]))
+        x = F.linear(x, Wd["linears_modulelist.%d.proj_2.weight" % l], Wd["linears_modulelist.%d.proj_2.bias" % l])
+        outs.append(x.permute(0, 2, 1).reshape(B, -1, h, w))                                           # :72
+    return F.conv2d(torch.cat(outs, dim=1), Wd["linear_fuse.weight"], Wd["linear_fuse.bias"])         # :74-75 (dropout: eval)
+
+
+def attn_pred(attn_fts, beta=1.0, gamma=3.0):
+    """model/model_excel.py:71-76."""
+    f = F.normalize(attn_fts.flatten(2).float(), dim=1)
+    a = f.transpose(2, 1).bmm(f)
+    return torch.sigmoid((a - torch.mean(a) * beta) * gamma)
+
+
 # --------------------------------------------------------------------------- attribute bank (a10)
 
 

@@ -84,3 +84,38 @@ def test_flip_merge_vs_reference_golden_and_oracle(golden):
     lam = lam - lam.amin(dim=(2, 3), keepdim=True)
     lam = (lam / (lam.amax(dim=(2, 3), keepdim=True) + 1e-5)).reshape(3, 20, 63).permute(0, 2, 1)
     assert (merge_flipped_maps(x.cuda(), 3, 7, 9).cpu() - lam).abs().max() < 1e-6
+
+
+class _MLP(torch.nn.Module):           # same attribute layout as model/segformer_head.py:12-26
+    def __init__(self, cin, e):
+        super().__init__()
+        self.proj, self.proj_2 = torch.nn.Linear(cin, e), torch.nn.Linear(e, e)
+
+
+class _Head(torch.nn.Module):          # same attribute layout as model/segformer_head.py:46-64
+    def __init__(self, cin, e, n):
+        super().__init__()
+        self.linears_modulelist = torch.nn.ModuleList([_MLP(cin, e) for _ in range(n)])
+        self.linear_fuse = torch.nn.Conv2d(e * n, e, kernel_size=1)
+
+
+def test_decoder_inference_vs_reference_golden(golden):
+    """SegFormerHead.forward + attn_pred (model/segformer_head.py:66-77, model/model_excel.py:71-76)."""
+    from excel_b200 import decoder
+    G, GL = golden("decoder"), golden("lvc")
+    head = _Head(TINY["width"], 32, TINY["layers"])
+    head.load_state_dict({k[5:]: t(v) for k, v in G.items() if k.startswith("head.")})
+    head = head.cuda().eval()
+    feats = t(GL["feats"])                                          # [L,B,N,D] as generate_clip_fts returns them
+    L, B, N, D = feats.shape
+    x_all = feats[:, :, 1:].permute(0, 1, 3, 2).reshape(L, B, D, 6, 6).cuda()
+    fts = decoder.segformer_head(head, x_all)
+    assert fts.shape == (B, 32, 6, 6)
+    assert (fts.cpu() - t(G["fts"])).abs().max() < 2e-5 * float(t(G["fts"]).abs().max())
+    # token-major entry point (no transposes: the form excel_model_forward uses), CLS rows included and dropped
+    fused = decoder.segformer_head_tokens(head, feats.reshape(L, B * N, D).cuda())
+    fts2 = fused.reshape(B, N, -1)[:, 1:].permute(0, 2, 1).reshape(B, -1, 6, 6)
+    assert (fts2.cpu() - t(G["fts"])).abs().max() < 2e-5 * float(t(G["fts"]).abs().max())
+    ap = decoder.attn_pred(t(G["fts"]).cuda())
+    assert (ap.cpu() - t(G["attn_pred"])).abs().max() < 1e-6
+    assert (port.attn_pred(t(G["fts"])) - t(G["attn_pred"])).abs().max() < 1e-6

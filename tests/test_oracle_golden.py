@@ -108,3 +108,18 @@ def test_lvc_branch_and_attrutils_oracle_vs_reference_golden(golden):
     assert (feats - t(G["feats"])).abs().max() < 2e-4
     assert (port.attrmap2clsmap(t(G["flag"]), t(G["amap"])) - t(G["clsmap"])).abs().max() < 1e-5
     assert (port.attr2cls_embedings(t(G["tf"]), t(G["bank"]), 20) - t(G["agg"])).abs().max() < 1e-6
+
+
+def test_decoder_inference_oracle_vs_reference_golden(golden):
+    """oracle/port.py segformer_head / attn_pred against the reference's module outputs."""
+    import torch
+    from oracle import port
+    from oracle.make_golden_cfg import TINY
+    G, GL = golden("decoder"), golden("lvc")
+    t = torch.from_numpy
+    Wd = {k[5:]: t(v) for k, v in G.items() if k.startswith("head.")}
+    feats = t(GL["feats"])
+    L, B, N, D = feats.shape
+    x_all = feats[:, :, 1:].permute(0, 1, 3, 2).reshape(L, B, D, 6, 6)
+    assert L == TINY["layers"] and (port.segformer_head(Wd, x_all) - t(G["fts"])).abs().max() < 1e-6
+    assert (port.attn_pred(t(G["fts"])) - t(G["attn_pred"])).abs().max() < 1e-6
