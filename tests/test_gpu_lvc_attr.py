@@ -119,3 +119,32 @@ def test_decoder_inference_vs_reference_golden(golden):
     ap = decoder.attn_pred(t(G["fts"]).cuda())
     assert (ap.cpu() - t(G["attn_pred"])).abs().max() < 1e-6
     assert (port.attn_pred(t(G["fts"])) - t(G["attn_pred"])).abs().max() < 1e-6
+
+
+def test_excel_model_forward_vs_oracle_composition():
+    """decoder.excel_model_forward (ExCEL_model.forward at inference, model/model_excel.py:48-77) == the oracle's pieces
+    composed the same way; the trained DecoderTransformer is stood in for by a fixed torch function."""
+    import types
+    from excel_b200 import decoder
+    from excel_b200.encoder import SurgeryViT
+    W = port.random_visual_weights(seed=3, **TINY)
+    torch.manual_seed(7)
+    head = _Head(TINY["width"], 32, TINY["layers"]).eval()
+    text_attr = synth.text_bank(45, TINY["embed"], seed=6).t().contiguous()            # model.text_attr: [E, T]
+    dec = lambda fts: (fts.mean(dim=1, keepdim=True), None)
+    model = types.SimpleNamespace(encoder=SurgeryViT(W), text_attr=text_attr.cuda(), num_classes=21,
+                                  decoder_fts_fuse=head.cuda(), decoder=dec)
+    imgs = synth.images(2, 96, seed=13)
+    seg, attn_fts, attr, attn_w, apred = decoder.excel_model_forward(model, imgs.cuda())
+    tok_r, attn_r, feats_r = port.generate_clip_fts(W, imgs)
+    attr_r = port.clip_feature_surgery(tok_r, text_attr.t())[:, 1:, :20]
+    x_all = feats_r[:, :, 1:].permute(0, 1, 3, 2).reshape(TINY["layers"], 2, TINY["width"], 6, 6)
+    fts_r = port.segformer_head({k: v.detach().cpu() for k, v in head.state_dict().items()}, x_all)
+    assert (attr.cpu() - attr_r).abs().max() < 1e-3 and (attn_w.cpu() - attn_r).abs().max() < 5e-5
+    assert (attn_fts.cpu() - fts_r).abs().max() < 1e-4 * float(fts_r.abs().max())
+    assert (seg.cpu() - fts_r.mean(dim=1, keepdim=True)).abs().max() < 1e-4 * float(fts_r.abs().max())
+    assert (apred.cpu() - port.attn_pred(fts_r)).abs().max() < 1e-4
+    # LVC call form: only attr_maps_raw comes back (model_excel.py:50-53)
+    out = decoder.excel_model_forward(model, imgs.cuda(), ex_feats=attn_fts)
+    tok_l, _, _ = port.generate_clip_fts(W, imgs, ex_feats=fts_r)
+    assert out.shape == attr.shape and (out.cpu() - port.clip_feature_surgery(tok_l, text_attr.t())[:, 1:, :20]).abs().max() < 1e-3
