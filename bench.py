@@ -238,7 +238,7 @@ def run_cuda(args):
     achieved, per_step_ms, nseg = par_rate(counts)
     by_planes = {str(c): round(par_rate([c] * BATCH)[0], 1) for c in (2, 3, 4)}
     traffic = None   # DRAM bytes of the same step from the committed ncu capture (profiles/), per step like `achieved`
-    tp = os.path.join(ROOT, "profiles", "r01f_par_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r01g_par_traffic.json")
     if os.path.exists(tp) and sorted(counts) == [2] * 8 + [3] * 7 + [4]:
         traffic = json.load(open(tp))["dram_bytes_per_step"]
     roofline = {"kernel": "par_iterate_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -246,7 +246,7 @@ def run_cuda(args):
                 "algorithmic_bytes": sum(4.0 * SIZE * SIZE * (48 + 2 * c) for c in counts),
                 "note": f"one propagation step over the {BATCH} images of a bench batch (planes/image {sorted(counts)}): "
                         f"{per_step_ms*1e3:.1f} us in {nseg} launches; uniform-C batches GB/s: {by_planes}; "
-                        "traffic = ncu dram bytes of the same three launches (profiles/r01f_par_traffic.json)"}
+                        "traffic = ncu dram bytes of the same three launches (profiles/r01g_par_traffic.json)"}
 
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
