@@ -46,7 +46,9 @@ __host__ __device__ constexpr size_t tc_smem(int bn) { return tc_stages(bn) * tc
 // TMA_EPI: the output leaves through TMA stores (fp32 tile: 4D map tmC; split-fp16: 3D map tmS) -- the epilogue
 // threads only move TMEM -> registers -> swizzled shared memory; otherwise (oddly pitched outputs) they store
 // to global themselves.
-template <int kBN, bool TMA_EPI>
+// RES: fp32 output with a residual term (its prefetch registers and control flow stay out of the other instantiations --
+// folding it into a run-time branch cost the GELU / split-output GEMM 20 % through code scheduling alone).
+template <int kBN, bool TMA_EPI, bool RES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmS, const TcParams p,
@@ -182,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int team_bar = 1 + team;
             // The residual slice of a chunk (this thread's row, 32 columns) is fetched one chunk AHEAD into rq[]: the global
             // round trip overlaps the previous chunk's staging / store and the TMEM wait instead of sitting between
-            // tcgen05.ld and the staging store (measured: out_proj 102 -> 66 us without the exposed loads).
+            // tcgen05.ld and the staging store (measured: out_proj 102 -> 90 us).
             float rq[32];
             auto fetch_residual = [&](int tt, int c) {
                 int m0, n0, z1, z2;
@@ -205,8 +207,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (c + 2 < kBN / 32) fetch_residual(tt, c + 2);
                 else if (tt + (int)gridDim.x < num_tiles) fetch_residual(tt + gridDim.x, team);
             };
-            const bool has_res = p.C != nullptr && p.residual != nullptr;
-            if (has_res && (int)blockIdx.x < num_tiles) fetch_residual(blockIdx.x, team);
+            constexpr bool has_res = RES;
+            if constexpr (has_res) {
+                if ((int)blockIdx.x < num_tiles) fetch_residual(blockIdx.x, team);
+            }
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++i) {
                 int m0, n0, z1, z2;
                 decode(t, m0, n0, z1, z2);
@@ -224,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     const int nb = n0 + c * 32;
                     if (nb >= p.N) {           // (team-uniform) nothing to store for this chunk
-                        if (has_res) fetch_next_residual(t, c);
+                        if constexpr (has_res) fetch_next_residual(t, c);
                         continue;
                     }
                     if (leader) tma_store_wait_read<0>();  // the store that last read the team's buffer has drained
@@ -234,13 +238,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < 32; ++j) {
                         float x = alpha * __uint_as_float(r[j]);
                         if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
-                        // QuickGELU x * sigmoid(1.702 x) (clip_surgery_model.py:280-282), exp2 domain
-                        if (act == 1) x = __fdividef(x, 1.f + exp2f(-2.4554669595930156f * x));
-                        else if (act == 2) x = fmaxf(x, 0.f);   // ReLU (model/segformer_head.py:24)
                         v[j] = x;
                     }
+                    // the activation as its own (warp-uniform) branch around a whole pass over the chunk: inside the element loop
+                    // a three-way choice was compiled to predicated code that ran the GELU's two MUFUs for every GEMM
+                    if (act == 1) {          // QuickGELU x * sigmoid(1.702 x) (clip_surgery_model.py:280-282), exp2 domain
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __fdividef(v[j], 1.f + exp2f(-2.4554669595930156f * v[j]));
+                    } else if (act == 2) {   // ReLU (model/segformer_head.py:24)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
                     if (p.C) {
-                        if (has_res) {
+                        if constexpr (has_res) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] += rq[j];
                             fetch_next_residual(t, c);
@@ -382,12 +392,14 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(256)));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(256)));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(128)));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(128)));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(64)));
-        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(64)));
+#define XL_TC_ATTR(BN_) \
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(BN_))); \
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(BN_))); \
+        XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(BN_)))
+        XL_TC_ATTR(256);
+        XL_TC_ATTR(128);
+        XL_TC_ATTR(64);
+#undef XL_TC_ATTR
         attr_set = true;
     }
     XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1 && batch % p.nb2 == 0,
@@ -427,10 +439,15 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
             tma_epi = true;
         }
     }
-#define XL_TC_LAUNCH(BN_, EPI_) gemm_tc_kernel<BN_, EPI_><<<grid, kTcThreads, tc_smem(BN_), st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
-    if (bn == 256) { if (tma_epi) XL_TC_LAUNCH(256, true); else XL_TC_LAUNCH(256, false); }
-    else if (bn == 128) { if (tma_epi) XL_TC_LAUNCH(128, true); else XL_TC_LAUNCH(128, false); }
-    else { if (tma_epi) XL_TC_LAUNCH(64, true); else XL_TC_LAUNCH(64, false); }
+    const bool res = tma_epi && p.C != nullptr && p.residual != nullptr;   // (the non-TMA fallback epilogue reads the residual itself)
+#define XL_TC_LAUNCH(BN_, EPI_, RES_) \
+    gemm_tc_kernel<BN_, EPI_, RES_><<<grid, kTcThreads, tc_smem(BN_), st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
+#define XL_TC_PICK(BN_) \
+    do { if (!tma_epi) XL_TC_LAUNCH(BN_, false, false); else if (res) XL_TC_LAUNCH(BN_, true, true); else XL_TC_LAUNCH(BN_, true, false); } while (0)
+    if (bn == 256) XL_TC_PICK(256);
+    else if (bn == 128) XL_TC_PICK(128);
+    else XL_TC_PICK(64);
+#undef XL_TC_PICK
 #undef XL_TC_LAUNCH
     return check_launch("gemm_tc_kernel");
 }
