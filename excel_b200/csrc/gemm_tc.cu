@@ -235,10 +235,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     bar_sync(team_bar, 128);
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = alpha * __uint_as_float(r[j]);
-                        if (bias && nb + j < p.N) x += __ldg(bias + nb + j);
-                        v[j] = x;
+                    for (int j = 0; j < 32; ++j) v[j] = alpha * __uint_as_float(r[j]);
+                    if (bias) {
+                        if (nb + 32 <= p.N && (reinterpret_cast<uintptr_t>(bias + nb) & 15) == 0) {   // (uniform) 8 x 16 B broadcast loads
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 q = __ldg(reinterpret_cast<const float4*>(bias + nb + j));
+                                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.N) v[j] += __ldg(bias + nb + j);
+                        }
                     }
                     // the activation as its own (warp-uniform) branch around a whole pass over the chunk: inside the element loop
                     // a three-way choice was compiled to predicated code that ran the GELU's two MUFUs for every GEMM
@@ -266,11 +275,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         uint8_t* sl = sb + 8192;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            __align__(16) __half h[8], l[8];
+                            __align__(16) __half2 h[4], l[4];   // packed conversions: one F2FP per pair
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                h[e] = __float2half_rn(v[8 * j + e]);
-                                l[e] = __float2half_rn(v[8 * j + e] - __half2float(h[e]));
+                            for (int e = 0; e < 4; ++e) {
+                                const float v0 = v[8 * j + 2 * e], v1 = v[8 * j + 2 * e + 1];
+                                h[e] = __floats2half2_rn(v0, v1);
+                                const float2 hf = __half22float2(h[e]);
+                                l[e] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
                             }
                             const int off = trow * 64 + ((j ^ ((trow >> 1) & 3)) << 4);
                             *reinterpret_cast<uint4*>(sh + off) = *reinterpret_cast<const uint4*>(h);
