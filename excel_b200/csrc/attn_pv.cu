@@ -69,7 +69,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXYStages; ++s) { mbar_init(&xy_full[s], 1); mbar_init(&xy_empty[s], 1); }
         for (int s = 0; s < kVStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], kPvEpiWarps); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_ready[s], kPvEpiWarps / 2); }
         mbar_init(o_full, 1);
         mbar_init(o_empty, kPvEpiWarps);
         fence_barrier_init();
@@ -86,7 +86,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // 64-key SUB-STEPS (the last key block of an image may hold <= 64 valid keys), each with its own 64-column S / P buffer:
     // four buffers in flight hide the MMA -> epilogue -> MMA round trip that a 128-key double buffer exposes.
     const int last_valid = p.N - (nblk - 1) * 128;          // valid keys of the last key block (1..128)
-    const int nsub_last = last_valid > 64 ? 2 : 1;
+    const int nsub_last = 2;   // every load step has both 64-key sub-steps (the second may hold no valid key): sub-step parity ==
+                               // key half, which is what lets the two epilogue groups below each own one half
 
     if (warp == 0) {
         // ---- TMA producer: the X / Y ring and the V^T ring advance independently (each polled without blocking), so a
@@ -177,8 +178,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             mbar_wait(&xy_full[s], (ls / kXYStages) & 1);
                             tc_fence_after();
                         }
-                        const int nvalid = min(64, p.N - qs.kb * 128 - qs.half * 64);
-                        const uint32_t idesc = make_idesc((nvalid + 15) & ~15);
+                        const int nvalid = min(64, p.N - qs.kb * 128 - qs.half * 64);   // may be <= 0: a 16-wide dummy tile
+                        const uint32_t idesc = make_idesc(nvalid > 0 ? (nvalid + 15) & ~15 : 16);
                         const uint32_t tacc = tmem_base + (gs & 3) * 64;
                         const uint32_t st = xy0 + s * kXYStage, yb = st + 2 * kTile + (uint32_t)qs.half * 8192u;   // Y rows 64..127: +64 x 128 B
                         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTile);
@@ -236,14 +237,16 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
     } else {
-        // ---- epilogue warps: warp (lg, qt) owns TMEM lanes 32*lg..+31 (query rows) and columns 16*qt..+15 of every 64-key
-        // sub-tile: S -> registers -> p -> split fp16 written back over the same 16 columns (hi pairs in +0..7, lo pairs
-        // in +8..15), so a warp only ever overwrites scores it has already read.
-        const int ew = warp - 2, lg = warp & 3, qt = ew >> 2;
+        // ---- epilogue warps in TWO GROUPS that ping-pong: group grp = qt / 2 owns the sub-tiles of key half grp (buffers grp and
+        // grp + 2), so while one group is in the latency-bound tail of a sub-tile (TMEM store, fence, barrier hand-off) the other
+        // is in the middle of the next one.  Warp (lg, grp, cq): TMEM lanes 32*lg..+31 (query rows), columns 32*cq..+31 of its
+        // group's 64-key sub-tiles, as two 16-column chunks: S -> registers -> p -> split fp16 written back over the same 16
+        // columns (hi pairs in +0..7, lo pairs in +8..15), so a warp only ever overwrites scores it has already read.
+        const int ew = warp - 2, lg = warp & 3, qt = ew >> 2, grp = qt >> 1, cq = qt & 1;
         const int trow = lg * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         float* stg = reinterpret_cast<float*>(stg_base) + ew * 512;   // warp-private 32 rows x 16 floats
-        uint32_t gu = 0, ngd = 0;
+        uint32_t gl = 0, ngd = 0;                                      // load steps seen: this group's sub-tile is 2 * gl + grp
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int rb = item % nblk, b = item / nblk;
             const int row = rb * 128 + trow;
@@ -253,55 +256,51 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const int hc = min(kHG, p.H - g * kHG);
                 const float* mrow = p.ml + ((int64_t)b * p.H + g * kHG) * p.N + row;   // + hh * N
                 for (int kb = 0; kb < nblk; ++kb) {
-                    const int nsub = kb < nblk - 1 ? 2 : nsub_last;
+                    const int key0 = kb * 128 + grp * 64 + cq * 32;   // this warp's 32 keys of the key block
                     float acc[2][16];
 #pragma unroll
-                    for (int hf = 0; hf < 2; ++hf)
+                    for (int c = 0; c < 2; ++c)
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) acc[hf][e] = 0.f;
+                        for (int e = 0; e < 16; ++e) acc[c][e] = 0.f;
                     float m_next = row_ok ? __ldg(mrow) : INFINITY;   // rows past N: exp2(-inf) = 0
-                    for (int hh = 0; hh < hc; ++hh) {
+                    for (int hh = 0; hh < hc; ++hh, ++gl) {
                         const float m_row = m_next;
                         if (row_ok && hh + 1 < hc) m_next = __ldg(mrow + (int64_t)(hh + 1) * p.N);
+                        const uint32_t u = 2 * gl + grp, buf = u & 3;
+                        mbar_wait(&s_full[buf], (u >> 2) & 1);
+                        tc_fence_after();
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            if (hf >= nsub) break;
-                            const int buf = gu & 3;
-                            mbar_wait(&s_full[buf], (gu >> 2) & 1);
-                            tc_fence_after();
-                            const int key0 = kb * 128 + hf * 64 + qt * 16;
-                            if (key0 < p.N && !(p.dbg & 2)) {     // (uniform) else: padding keys only, neither the S nor the P columns are used
-                                const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + qt * 16);
-                                uint32_t r[16];
-                                tmem_ld16(taddr, r);
-                                if (key0 + 16 > p.N) {
+                        for (int c = 0; c < 2; ++c) {
+                            if (key0 + c * 16 >= p.N || (p.dbg & 2)) break;   // (uniform) padding keys only: columns unused
+                            const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + cq * 32 + c * 16);
+                            uint32_t r[16];
+                            tmem_ld16(taddr, r);
+                            if (key0 + c * 16 + 16 > p.N) {
 #pragma unroll
-                                    for (int e = 0; e < 16; ++e)
-                                        if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
-                                }
-                                uint32_t ph[8], pl[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
-                                    const float v0 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e]), -m_row));
-                                    const float v1 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e + 1]), -m_row));
-                                    acc[hf][2 * e] += v0;
-                                    acc[hf][2 * e + 1] += v1;
-                                    const __half2 hh2 = __floats2half2_rn(v0, v1);
-                                    const float2 hf2 = __half22float2(hh2);
-                                    const __half2 ll2 = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
-                                    ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
-                                    pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
-                                }
-                                tmem_st8(taddr, ph);       // P_hi: keys (2e, 2e+1) of the chunk in column e
-                                tmem_st8(taddr + 8, pl);   // P_lo
-                                tmem_st_wait();
+                                for (int e = 0; e < 16; ++e)
+                                    if (key0 + c * 16 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
                             }
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&p_ready[buf]);
-                            ++gu;
+                            uint32_t ph[8], pl[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
+                                const float v0 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e]), -m_row));
+                                const float v1 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e + 1]), -m_row));
+                                acc[c][2 * e] += v0;
+                                acc[c][2 * e + 1] += v1;
+                                const __half2 hh2 = __floats2half2_rn(v0, v1);
+                                const float2 hf2 = __half22float2(hh2);
+                                const __half2 ll2 = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
+                                ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
+                                pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
+                            }
+                            tmem_st8(taddr, ph);       // P_hi: keys (2e, 2e+1) of the chunk in column e
+                            tmem_st8(taddr + 8, pl);   // P_lo
                         }
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&p_ready[buf]);
                     }
                     // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
                     // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
@@ -309,15 +308,15 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if (nrow > 0 && !(p.dbg & 4)) {
                         const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const int kc = kb * 128 + hf * 64 + qt * 16;
+                        for (int c = 0; c < 2; ++c) {
+                            const int kc = key0 + c * 16;
                             if (kc >= p.N) break;   // (uniform)
                             if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
                             __syncwarp();
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
                                 *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-                                    make_float4(cf * acc[hf][4 * j], cf * acc[hf][4 * j + 1], cf * acc[hf][4 * j + 2], cf * acc[hf][4 * j + 3]);
+                                    make_float4(cf * acc[c][4 * j], cf * acc[c][4 * j + 1], cf * acc[c][4 * j + 2], cf * acc[c][4 * j + 3]);
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
