@@ -75,7 +75,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         for (int s = 0; s < kAAcc; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kAEpiWarps);  // one arrival per epilogue warp
+            mbar_init(&acc_empty[s], MODE == 0 ? kAEpiWarps / 2 : kAEpiWarps);  // one arrival per epilogue warp that reads the tile
         }
         fence_barrier_init();
     }
@@ -198,21 +198,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const int hn = j + 1, ty = hn / p.H, hd = hn - ty * p.H;
                     m_next = __ldg(p.m + (((int64_t)ty * p.B + b) * p.H + hd) * p.N + row);
                 }
-                mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
-                tc_fence_after();
-                const int key0 = kb * 128 + qt * 32;
-                if (key0 < p.N) {   // (uniform) else: padding keys only -- not even computed by the MMA
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + qt * 32), r);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp's TMEM reads of the tile are done
-                    if (key0 + 32 > p.N) {
+                if (MODE == 0) {
+                    // Two groups of 8 warps ping-pong over the tiles (group = tile parity): while one group is in the TMEM
+                    // round trip / barrier hand-off of a tile the other is in the exp2 stream of the previous one.  A warp
+                    // covers 64 columns (cq) of its group's tiles as two 32-column chunks.
+                    const int grp = qt >> 1, cq = qt & 1;
+                    if ((it & 1) != grp) continue;
+                    mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
+                    tc_fence_after();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e)
-                            if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf: padding keys drop out of max and sum
-                    }
-                    if (MODE == 0) {
+                    for (int c = 0; c < 2; ++c) {
+                        const int key0 = kb * 128 + cq * 64 + c * 32;
+                        uint32_t r[32];
+                        if (key0 < p.N)   // (uniform) else: padding keys only -- not even computed by the MMA
+                            tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + cq * 64 + c * 32), r);
+                        if (c == 1) {     // this warp's TMEM reads of the tile are done
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                        }
+                        if (key0 >= p.N) continue;
+                        if (key0 + 32 > p.N) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e)
+                                if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf: padding keys drop out of max and sum
+                        }
                         // running row max / sum in the exp2 domain; alpha > 0, so max(alpha*a) = alpha*max(a).
                         // Four independent max / sum chains keep the FMNMX / FADD latency off the critical path.
                         float c0 = -INFINITY, c1 = -INFINITY, c2 = -INFINITY, c3 = -INFINITY;
@@ -236,11 +246,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             l_run = l_run * ex2_approx(m_run - m_new) + ((s0 + s1) + (s2 + s3));
                             m_run = m_new;
                         }
-                    } else {
-                        // 2^10 p = exp2(alpha*s - (m + log2 l - 10)): one FFMA + one MUFU + one FADD per element
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) acc[e] += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_row));
                     }
+                    continue;
+                }
+                mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
+                tc_fence_after();
+                const int key0 = kb * 128 + qt * 32;
+                if (key0 < p.N) {   // (uniform) else: padding keys only -- not even computed by the MMA
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + qt * 32), r);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp's TMEM reads of the tile are done
+                    if (key0 + 32 > p.N) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e)
+                            if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
+                    }
+                    // 2^10 p = exp2(alpha*s - (m + log2 l - 10)): one FFMA + one MUFU + one FADD per element
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) acc[e] += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_row));
                 } else {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
