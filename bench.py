@@ -192,7 +192,8 @@ def run_cuda(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), launches, (sampler.stop() if sampler else None), out
 
-    ms, launches, clocks, labels = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    # clocks / throttle reasons are sampled on rank 0's GPU only (one nvidia-smi poller per job, not per rank)
+    ms, launches, clocks, labels = timed(step_resident, args.steps, args.warmup, sample_clocks=(rank == 0))
     value = world * BATCH * args.steps / (ms / 1e3)
     ms_e, _, _, labels_e = timed(step_e2e, args.steps, max(args.warmup, 3), finish=pipe.flush)
     assert labels_e is not None and labels_e.shape == (BATCH, SIZE, SIZE) and not labels_e.is_cuda
