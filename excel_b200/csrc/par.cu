@@ -224,7 +224,7 @@ __device__ __forceinline__ void load4_shift(uint32_t p, float (&m)[4]) {
 // as: byte address of this thread's affinities in the stage; ctr[c]: byte address of its centre pixel in
 // plane c; d4 / dW4: byte offsets of one dilation step in x / y.
 template <int CCH, int TY, int KG, int MODE>
-__device__ __forceinline__ void par_taps(int t0, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float (&acc)[4][CCH]) {
+__device__ __forceinline__ void par_taps(int t0, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4, float2 (&acc)[2][CCH]) {
 #pragma unroll
     for (int tt = 0; tt < KG; ++tt) {
         const int t = t0 + tt;  // compile-time after unrolling (the caller's q loop is unrolled too)
@@ -246,14 +246,16 @@ __device__ __forceinline__ void par_taps(int t0, uint32_t as, const uint32_t (&c
                 m[0] = lds32(p); m[1] = lds32(p + 4); m[2] = lds32(p + 8); m[3] = lds32(p + 12);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i][c] = fmaf(a[i], m[i], acc[i][c]);
+            // packed fp32x2 FMAs (sm_100 FFMA2: the scalar FFMA issues at half rate): same two IEEE fmas per instruction
+            acc[0][c] = __ffma2_rn(make_float2(a[0], a[1]), make_float2(m[0], m[1]), acc[0][c]);
+            acc[1][c] = __ffma2_rn(make_float2(a[2], a[3]), make_float2(m[2], m[3]), acc[1][c]);
         }
     }
 }
 
 template <int CCH, int TY, int KG>
 __device__ __forceinline__ void par_taps_mode(int mode, int t0, uint32_t as, const uint32_t (&ctr)[CCH], int d4, int dW4,
-                                              float (&acc)[4][CCH]) {
+                                              float2 (&acc)[2][CCH]) {
     if (mode == 0) par_taps<CCH, TY, KG, 0>(t0, as, ctr, d4, dW4, acc);
     else if (mode == 1) par_taps<CCH, TY, KG, 1>(t0, as, ctr, d4, dW4, acc);
     else if (mode == 2) par_taps<CCH, TY, KG, 2>(t0, as, ctr, d4, dW4, acc);
@@ -368,11 +370,11 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
             cp_async_wait_all();
             bar_sync(1, NC);
         }
-        float acc[4][CCH];
+        float2 acc[2][CCH];   // pixels (0,1) and (2,3) of the thread's quad
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int c = 0; c < CCH; ++c) acc[i][c] = 0.f;
+            for (int c = 0; c < CCH; ++c) acc[i][c] = make_float2(0.f, 0.f);
         auto round = [&](int d) {   // the 8 taps of one dilation, KG per ring stage
             const int d4 = d * 4, dW4 = d * TW * 4;
             const int mode = d == 1 ? 1 : (d == 2 ? 2 : ((d & 3) == 0 ? 0 : -1));
@@ -406,11 +408,11 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
                 if (c >= np) break;
                 float* o = out + (int64_t)(pc + c) * plane + (int64_t)y * W + x;
                 if (x + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                    *reinterpret_cast<float4*>(o) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+                    *reinterpret_cast<float4*>(o) = make_float4(acc[0][c].x, acc[0][c].y, acc[1][c].x, acc[1][c].y);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (x + i < W) o[i] = acc[i][c];
+                        if (x + i < W) o[i] = (i & 1) ? acc[i >> 1][c].y : acc[i >> 1][c].x;
                 }
             }
         }
