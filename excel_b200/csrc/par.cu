@@ -115,36 +115,49 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
         if (y >= H) break;
         const float* ctr = s0p + 8 * j * TW;
         const float c0 = ctr[0], c1 = ctr[cs], c2 = ctr[2 * cs];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+        // The arithmetic runs on packed fp32x2 instructions (sm_100 FADD2 / FMUL2 / FFMA2 -- scalar FP32 issues at half rate and
+        // this kernel is bound by the FMA pipe): taps t and t+1 of a dilation share one instruction per channel.
+        float2 S0 = make_float2(0.f, 0.f), S1 = S0, S2 = S0, Q0 = S0, Q1 = S0, Q2 = S0;
 #pragma unroll
         for (int di = 0; di < NDIL; ++di) {
             const int d = STD ? kStdDil[di] : g.dil[di], dW = d * TW;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
-                const float d0 = p[0] - c0, d1 = p[cs] - c1, d2 = p[2 * cs] - c2;
-                s0 += d0; q0 = fmaf(d0, d0, q0);
-                s1 += d1; q1 = fmaf(d1, d1, q1);
-                s2 += d2; q2 = fmaf(d2, d2, q2);
+            for (int t = 0; t < 8; t += 2) {
+                const float* pa = ctr + tap_dy(t) * dW + tap_dx(t) * d;
+                const float* pb = ctr + tap_dy(t + 1) * dW + tap_dx(t + 1) * d;
+                const float2 D0 = __fadd2_rn(make_float2(pa[0], pb[0]), make_float2(-c0, -c0));
+                const float2 D1 = __fadd2_rn(make_float2(pa[cs], pb[cs]), make_float2(-c1, -c1));
+                const float2 D2 = __fadd2_rn(make_float2(pa[2 * cs], pb[2 * cs]), make_float2(-c2, -c2));
+                S0 = __fadd2_rn(S0, D0); Q0 = __ffma2_rn(D0, D0, Q0);
+                S1 = __fadd2_rn(S1, D1); Q1 = __ffma2_rn(D1, D1, Q1);
+                S2 = __fadd2_rn(S2, D2); Q2 = __ffma2_rn(D2, D2, Q2);
             }
         }
+        const float s0 = S0.x + S0.y, s1 = S1.x + S1.y, s2 = S2.x + S2.y;
+        const float q0 = Q0.x + Q0.y, q1 = Q1.x + Q1.y, q2 = Q2.x + Q2.y;
         const float r0 = invw / (sqrtf(fmaxf((q0 - s0 * s0 * invk) * invk1, 0.f)) + 1e-8f);
         const float r1 = invw / (sqrtf(fmaxf((q1 - s1 * s1 * invk) * invk1, 0.f)) + 1e-8f);
         const float r2 = invw / (sqrtf(fmaxf((q2 - s2 * s2 * invk) * invk1, 0.f)) + 1e-8f);
         float a[K];
         float amax = -INFINITY;
+        const float2 R0 = make_float2(r0, r0), R1 = make_float2(r1, r1), R2 = make_float2(r2, r2);
+        // -mean_c(t^2) * log2(e) (exp2 below); the channel mean as a multiplication: a true division costs a
+        // ~10-instruction slow-path check 48 times per pixel for at most 1 ulp of the exponent
+        const float2 KK = make_float2(-1.4426950408889634f / 3.f, -1.4426950408889634f / 3.f);
 #pragma unroll
         for (int di = 0; di < NDIL; ++di) {
             const int d = STD ? kStdDil[di] : g.dil[di], dW = d * TW;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const float* p = ctr + tap_dy(t) * dW + tap_dx(t) * d;
-                const float t0 = (p[0] - c0) * r0, t1 = (p[cs] - c1) * r1, t2 = (p[2 * cs] - c2) * r2;
-                // -mean_c(t^2) * log2(e) (exp2 below); the channel mean as a multiplication: a true division costs a
-                // ~10-instruction slow-path check 48 times per pixel for at most 1 ulp of the exponent
-                const float v = (t0 * t0 + t1 * t1 + t2 * t2) * (-1.4426950408889634f / 3.f);
-                a[di * 8 + t] = v;
-                amax = fmaxf(amax, v);
+            for (int t = 0; t < 8; t += 2) {
+                const float* pa = ctr + tap_dy(t) * dW + tap_dx(t) * d;
+                const float* pb = ctr + tap_dy(t + 1) * dW + tap_dx(t + 1) * d;
+                const float2 T0 = __fmul2_rn(__fadd2_rn(make_float2(pa[0], pb[0]), make_float2(-c0, -c0)), R0);
+                const float2 T1 = __fmul2_rn(__fadd2_rn(make_float2(pa[cs], pb[cs]), make_float2(-c1, -c1)), R1);
+                const float2 T2 = __fmul2_rn(__fadd2_rn(make_float2(pa[2 * cs], pb[2 * cs]), make_float2(-c2, -c2)), R2);
+                const float2 V = __fmul2_rn(__ffma2_rn(T2, T2, __ffma2_rn(T1, T1, __fmul2_rn(T0, T0))), KK);
+                a[di * 8 + t] = V.x;
+                a[di * 8 + t + 1] = V.y;
+                amax = fmaxf(amax, fmaxf(V.x, V.y));
             }
         }
         float sum = 0.f;
