@@ -235,15 +235,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         }
                         const float m_new = fmaxf(m_run, p.alpha * fmaxf(fmaxf(c0, c1), fmaxf(c2, c3)));
                         if (m_new > -INFINITY) {
-                            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                            // packed fp32x2 FMA / ADD (sm_100: scalar FP32 issues at half rate); four independent sum chains
+                            const float2 al = make_float2(p.alpha, p.alpha), mm = make_float2(-m_new, -m_new);
+                            float2 sa = make_float2(0.f, 0.f), sb = sa;
 #pragma unroll
                             for (int e = 0; e < 32; e += 4) {
-                                s0 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e]), -m_new));
-                                s1 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 1]), -m_new));
-                                s2 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 2]), -m_new));
-                                s3 += ex2_approx(fmaf(p.alpha, __uint_as_float(r[e + 3]), -m_new));
+                                const float2 xa = __ffma2_rn(al, make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), mm);
+                                const float2 xb = __ffma2_rn(al, make_float2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), mm);
+                                sa = __fadd2_rn(sa, make_float2(ex2_approx(xa.x), ex2_approx(xa.y)));
+                                sb = __fadd2_rn(sb, make_float2(ex2_approx(xb.x), ex2_approx(xb.y)));
                             }
-                            l_run = l_run * ex2_approx(m_run - m_new) + ((s0 + s1) + (s2 + s3));
+                            l_run = l_run * ex2_approx(m_run - m_new) + ((sa.x + sb.x) + (sa.y + sb.y));
                             m_run = m_new;
                         }
                     }
