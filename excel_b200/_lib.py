@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libexcel_b200.so")
+LIB_PATH = os.environ.get("EXCEL_B200_LIB") or os.path.join(_HERE, "lib", "libexcel_b200.so")   # (env override: A/B builds)
 
 _c = ctypes
 _i, _i64, _f, _p = _c.c_int, _c.c_int64, _c.c_float, _c.c_void_p

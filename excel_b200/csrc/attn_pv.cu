@@ -284,13 +284,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
-                                const float v0 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e]), -m_row));
-                                const float v1 = ex2a(fmaf(p.alpha, __uint_as_float(r[2 * e + 1]), -m_row));
-                                acc[c][2 * e] += v0;
-                                acc[c][2 * e + 1] += v1;
-                                const __half2 hh2 = __floats2half2_rn(v0, v1);
+                                // (packed fp32x2 FMA / ADD: scalar FP32 issues at half rate on sm_100)
+                                const float2 x = __ffma2_rn(make_float2(p.alpha, p.alpha),
+                                                            make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])),
+                                                            make_float2(-m_row, -m_row));
+                                const float2 v = make_float2(ex2a(x.x), ex2a(x.y));
+                                const float2 a2 = __fadd2_rn(make_float2(acc[c][2 * e], acc[c][2 * e + 1]), v);
+                                acc[c][2 * e] = a2.x;
+                                acc[c][2 * e + 1] = a2.y;
+                                const __half2 hh2 = __floats2half2_rn(v.x, v.y);
                                 const float2 hf2 = __half22float2(hh2);
-                                const __half2 ll2 = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
+                                const float2 lo2 = __fadd2_rn(v, make_float2(-hf2.x, -hf2.y));
+                                const __half2 ll2 = __floats2half2_rn(lo2.x, lo2.y);
                                 ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
                                 pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
                             }
