@@ -4,18 +4,22 @@
 // clip/clip_surgery_model.py:101-102,151-154,297-307).
 //
 // Given the softmax row statistics of the stats pass (attn_tc.cu, MODE 0) a CTA owns one 128-row query block of one
-// image and walks  head group (4 heads) -> key block (128 keys) -> head:
-//   S  = X_h Y_h^T                     split-fp16 operands from shared memory (TMA), 3 MMA passes, fp32 in TMEM;
+// image and walks  head group (4 heads) -> key block (128 keys) -> head -> 64-key half:
+//   S  = X_h Y_h^T                     split-fp16 operands from shared memory (TMA), 3 MMA passes, fp32 in TMEM
+//                                      (64-key sub-tiles: four 64-column S / P buffers in flight);
 //   p  = exp2(alpha s - (m + log2 l))  exactly normalised, in the epilogue warps; summed over the heads in registers
 //                                      (-> the attention map the API returns) and written BACK INTO THE S TILE's
 //                                      tensor memory as split fp16 (hi | lo pairs, two keys per 32-bit column);
-//   O_h += P V_h                       tcgen05.mma with the A operand read from TENSOR MEMORY and V_h^T from shared
-//                                      memory (3 passes: P_hi V_lo + P_lo V_hi + P_hi V_hi), fp32 accumulators of the
-//                                      4 heads of the group in the other half of TMEM (4 x 64 columns).
-// TMEM budget: 2 x 128 columns (S / P double buffer) + 256 columns (O of 4 heads) = 512.  The map is written once
-// per (head group, key block): plain stores for the first group, same-thread read-modify-write for the others (a
-// fixed summation order, so the result is deterministic).  The last key block of an image (N = 128 q + r) runs with
-// the MMA N / K extents rounded up to 16 instead of 128.
+//   O_h += P V_h                       tcgen05.mma with the A operand read from TENSOR MEMORY and V_h [keys, head dim]
+//                                      as an MN-major shared-memory operand straight from the qkv matrix (3 passes:
+//                                      P_hi V_lo + P_lo V_hi + P_hi V_hi), fp32 accumulators of the 4 heads of the
+//                                      group in the other half of TMEM (4 x 64 columns).
+// TMEM budget: 4 x 64 columns (S / P) + 256 columns (O of 4 heads) = 512.  Warps: TMA producer (X / Y ring and V ring
+// polled independently), MMA issuer (S runs up to four sub-steps ahead of P V), 16 epilogue warps in two groups that
+// ping-pong over the key halves.  The head-reduced map leaves once per (head group, key block) through the warp's staging
+// block and TMA: a plain store for the first head group, a reduce-add in L2 for the others (fixed order per address, so
+// the result is bit-reproducible), into a row-padded scratch [B,N,Npad] that attn_compact_kernel rewrites to [B,N,N].
+// Key blocks are trimmed to the valid keys rounded up to 16 (N = 1025: the ninth block is one 16-wide MMA).
 #include <cuda_fp16.h>
 
 #include "attn_tc.cuh"

@@ -10,9 +10,10 @@
 //   MODE 1 (map): per (b, row block, key block) walk the (score set, head) pairs: S tile again, p = exp2(alpha s - stat),
 //           summed in registers and written once as coef * sum p through a TMA store into the row-padded map [B,N,Npad].
 // Skeleton = the persistent GEMM's (gemm_tc.cu): TMA producer warp, elected-lane tcgen05.mma issuer, FOUR TMEM
-// accumulators (512 columns) so that the MMA -> epilogue round trip stays off the critical path; 16 epilogue warps (four
-// per TMEM lane group, 32 columns of every tile each).  The last key block of an image (N = 128 q + r) runs with the
-// MMA N extent rounded up to 16.
+// accumulators (512 columns) so that the MMA -> epilogue round trip stays off the critical path; 16 epilogue warps, four
+// per TMEM lane group (MODE 0: two groups of 8 ping-pong over the tiles, 64 columns per warp, the item's X tile resident
+// in shared memory beside a Y-only ring; MODE 1: all 16 on every tile, 32 columns each).  The last key block of an image
+// (N = 128 q + r) runs with the MMA N extent rounded up to 16.
 #include <cuda_fp16.h>
 
 #include "attn_tc.cuh"
