@@ -11,13 +11,14 @@
 // of 64, padding zero.  Both operands are K-major ("TN": C[m,n] = sum_k A[m,k] B[n,k]), i.e. activations
 // [tokens, features] against nn.Linear weights [out, in], q against k, P against V^T.
 //
-// Kernel anatomy (one 128x128 output tile per CTA, 192 threads):
-//   warp 0   : TMA producer -- 4 boxes (A_hi, A_lo, B_hi, B_lo; 64 k x 128 rows, 128B swizzle) per stage,
-//              3-stage mbarrier ring (64 KB / stage);
-//   warp 1   : allocates 128 TMEM columns, one lane issues 12 tcgen05.mma (M128 N128 K16, kind::f16) per
-//              stage and tcgen05.commit's the stage back to the producer / the accumulator to the epilogue;
-//   warps 2-5: epilogue -- tcgen05.ld 32 lanes x 32 columns per instruction, alpha / bias / QuickGELU /
-//              residual in registers, fp32 and/or split-fp16 stores.
+// Kernel anatomy (persistent: one CTA per SM walks 128 x BN output tiles, BN = 64 / 128 / 256; 320 threads):
+//   warp 0   : TMA producer -- A_hi, A_lo (64 k x 128 rows) and B_hi, B_lo (64 k x BN rows, or 64-column x 64-row boxes of
+//              an MN-major B) per stage, 128B swizzle, 3-stage mbarrier ring (2 stages of 96 KB at BN = 256);
+//   warp 1   : allocates 2 x BN TMEM columns (two accumulators); its elected lane issues 12 tcgen05.mma
+//              (M128 x BN x K16, kind::f16) per stage and tcgen05.commit's the stage back to the producer / the finished
+//              accumulator to the epilogue, which then overlaps the next tile's main loop;
+//   warps 2-9: epilogue, two teams of four warps on alternate 32-column chunks -- tcgen05.ld 32 lanes x 32 columns,
+//              alpha / bias / QuickGELU or ReLU / residual in registers, swizzled staging, TMA store (fp32 or split fp16).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
