@@ -129,3 +129,39 @@ def test_merge_flipped_maps_has_no_cpu_path():
     from excel_b200.camutils import merge_flipped_maps
     with pytest.raises(RuntimeError):
         merge_flipped_maps(torch.rand(4, 36, 20), 2, 6, 6)
+
+
+def test_segments_group_runs_of_equal_plane_count():
+    from excel_b200.affutils import _segments
+    assert _segments([2, 2, 3, 3, 3, 4, 5, 7]) == [(0, 2, 2), (2, 5, 3), (5, 6, 4), (6, 8, 7)]
+    assert _segments([3]) == [(0, 1, 3)]
+    assert _segments([6, 6, 9]) == [(0, 3, 9)]       # everything above 4 planes shares one run (passes of 3 planes)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle port): one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0 and line["higher_is_better"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("ViT-B/16 CAM+SVC+PAR")
+
+
+def test_bench_cuda_arm_fails_loudly_without_gpu():
+    """No GPU here: the product arm must raise, not fall back to a CPU path."""
+    import subprocess
+    import sys
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "images/s" not in r.stdout
