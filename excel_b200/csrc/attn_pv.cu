@@ -22,6 +22,8 @@
 // Key blocks are trimmed to the valid keys rounded up to 16 (N = 1025: the ninth block is one 16-wide MMA).
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "attn_tc.cuh"
 #include "common.cuh"
 #include "excel_b200.h"
@@ -273,13 +275,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const uint32_t u = 2 * gl + grp, buf = u & 3;
                         mbar_wait(&s_full[buf], (u >> 2) & 1);
                         tc_fence_after();
+                        // Only the LAST key block of an image can hold padding keys.  The two cases are separate instantiations of the
+                        // chunk code: written as one body, the per-element `key >= N ? -inf : s` test was if-converted and ran
+                        // (ISETP + SEL per element, a quarter of the epilogue's instructions) for every key block.
+                        auto chunks = [&](auto tail_tag) {
+                        constexpr bool TAIL = decltype(tail_tag)::value;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            if (key0 + c * 16 >= p.N || (p.dbg & 2)) break;   // (uniform) padding keys only: columns unused
+                            if ((TAIL && key0 + c * 16 >= p.N) || (p.dbg & 2)) break;   // (uniform) padding keys only: columns unused
                             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + cq * 32 + c * 16);
                             uint32_t r[16];
                             tmem_ld16(taddr, r);
-                            if (key0 + c * 16 + 16 > p.N) {
+                            if constexpr (TAIL) {
 #pragma unroll
                                 for (int e = 0; e < 16; ++e)
                                     if (key0 + c * 16 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
@@ -306,6 +313,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             tmem_st8(taddr, ph);       // P_hi: keys (2e, 2e+1) of the chunk in column e
                             tmem_st8(taddr + 8, pl);   // P_lo
                         }
+                        };
+                        if (kb == nblk - 1) chunks(std::true_type{});
+                        else chunks(std::false_type{});
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();

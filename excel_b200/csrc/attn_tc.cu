@@ -16,6 +16,8 @@
 // (N = 128 q + r) runs with the MMA N extent rounded up to 16.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "attn_tc.cuh"
 #include "common.cuh"
 #include "excel_b200.h"
@@ -207,19 +209,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if ((it & 1) != grp) continue;
                     mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
                     tc_fence_after();
+                    // Only the LAST key block can hold padding keys: the chunk code is instantiated twice so that the per-element
+                    // `key >= N ? -inf : s` selection (if-converted by the compiler) does not run for the other key blocks.
+                    auto chunks = [&](auto tail_tag) {
+                    constexpr bool TAIL = decltype(tail_tag)::value;
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         const int key0 = kb * 128 + cq * 64 + c * 32;
                         uint32_t r[32];
-                        if (key0 < p.N)   // (uniform) else: padding keys only -- not even computed by the MMA
+                        if (!TAIL || key0 < p.N)   // (uniform) else: padding keys only -- not even computed by the MMA
                             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + cq * 64 + c * 32), r);
                         if (c == 1) {     // this warp's TMEM reads of the tile are done
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&acc_empty[buf]);
                         }
-                        if (key0 >= p.N) continue;
-                        if (key0 + 32 > p.N) {
+                        if (TAIL && key0 >= p.N) continue;
+                        if constexpr (TAIL) {
 #pragma unroll
                             for (int e = 0; e < 32; ++e)
                                 if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf: padding keys drop out of max and sum
@@ -250,18 +256,23 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             m_run = m_new;
                         }
                     }
+                    };
+                    if (kb == nblk - 1) chunks(std::true_type{});
+                    else chunks(std::false_type{});
                     continue;
                 }
                 mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
                 tc_fence_after();
                 const int key0 = kb * 128 + qt * 32;
-                if (key0 < p.N) {   // (uniform) else: padding keys only -- not even computed by the MMA
+                auto tile = [&](auto tail_tag) {   // (two instantiations: see MODE 0)
+                constexpr bool TAIL = decltype(tail_tag)::value;
+                if (!TAIL || key0 < p.N) {   // (uniform) else: padding keys only -- not even computed by the MMA
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + qt * 32), r);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);   // this warp's TMEM reads of the tile are done
-                    if (key0 + 32 > p.N) {
+                    if constexpr (TAIL) {
 #pragma unroll
                         for (int e = 0; e < 32; ++e)
                             if (key0 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
@@ -273,6 +284,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
+                };
+                if (kb == nblk - 1) tile(std::true_type{});
+                else tile(std::false_type{});
             }
             if (MODE == 0) {
                 // merge the four column quarters of each row; write m + log2(l) - 10 (what the map / P V passes subtract)
