@@ -4,12 +4,13 @@ The product path is CUDA only: if libexcel_b200.so is missing or a call fails th
 no CPU or PyTorch fallback behind any shim in this package.
 """
 import ctypes
+import functools
 import os
 
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("EXCEL_B200_LIB") or os.path.join(_HERE, "lib", "libexcel_b200.so")   # (env override: A/B builds)
+LIB_PATH = os.path.join(_HERE, "lib", "libexcel_b200.so")
 
 _c = ctypes
 _i, _i64, _f, _p = _c.c_int, _c.c_int64, _c.c_float, _c.c_void_p
@@ -98,6 +99,30 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def _first_cuda_tensor(values):
+    for a in values:
+        if torch.is_tensor(a):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, (list, tuple)) and a and torch.is_tensor(a[0]) and a[0].is_cuda:
+            return a[0]
+    return None
+
+
+def on_tensor_device(fn):
+    """Decorator of the public shims: run `fn` with the device of its first CUDA-tensor argument current, so that
+    `stream()` / the kernel launches / the function attributes land on the tensors' device, not on whatever device the
+    caller left current (tensors on cuda:1 with cuda:0 current)."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = _first_cuda_tensor(list(args) + list(kwargs.values()))
+        if t is not None and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
 
 
 def f32c(t):

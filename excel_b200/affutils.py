@@ -64,6 +64,7 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, orde
     return out
 
 
+@_lib.on_tensor_device
 def compute_trans_mat(attn_weight):
     """utils/affutils.py:8-24 for one [n_p,n_p] attention matrix (materialises T@T; the pipeline does not)."""
     A = _lib.f32c(attn_weight)
@@ -80,6 +81,7 @@ def compute_trans_mat(attn_weight):
     return T2
 
 
+@_lib.on_tensor_device
 def box_masks(attr_maps, cls_lists, gh, gw, caa_thre):
     """utils/affutils.py:26-53 + :209-212 on the device: [Q, gh, gw] masks for the (image, class) pairs."""
     dev = attr_maps.device
@@ -96,6 +98,7 @@ def box_masks(attr_maps, cls_lists, gh, gw, caa_thre):
     return m.view(Q, gh, gw)
 
 
+@_lib.on_tensor_device
 def refine_cams_with_aff(attr_map, attn_weights, cls_label, size, caa_thre=0.79, attn_layers=6, seg_attn=None):
     """Same contract as utils/affutils.py:177-223: returns (list of n [h//16, w//16] CUDA tensors,
     int64 class indices on the CPU)."""
@@ -121,6 +124,7 @@ def _cams_to_planes(refined, counts, gh, gw, H, W):
     return planes, plane_off, off
 
 
+@_lib.on_tensor_device
 def refine_cams_with_bkg_weclip(cam_refined_list, inputs_denorm, cls_lst, par, size):
     """Same contract as utils/affutils.py:161-174: (labels [1,H,W] int64, cams [C,H,W] fp32).
     ``size`` is (H, W) like at the reference's call sites (the reference unpacks it as ``w, h`` and swaps
@@ -150,6 +154,7 @@ def _segments(counts):
     return segs
 
 
+@_lib.on_tensor_device
 def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=None, caa_thre=0.79, attn_layers=6,
                  return_cams=False, cls_lists=None):
     """Fused batched SVC + PAR + argmax (tools/infer_lam.py:88-94 for the whole batch).

@@ -31,6 +31,7 @@ def load_text_attri(pt_path):
     return text_attri.float().cuda(), attri_flag.cuda()
 
 
+@_lib.on_tensor_device
 def attrmap2clsmap(attri_flag, attr_maps):
     """utils/attrutils.py:11-17: attr_maps [B,n_p,A] @ attri_flag[cls,A]^T -> [B,n_p,cls]."""
     B, n_p, A = attr_maps.shape
@@ -38,6 +39,7 @@ def attrmap2clsmap(attri_flag, attr_maps):
     return out.view(B, n_p, -1)
 
 
+@_lib.on_tensor_device
 def attr2cls_embedings(text_features, text_attri, num_classes):
     """utils/attrutils.py:19-29: softmax(fg_text @ bank) @ bank^T + fg_text, background rows appended, rows
     L2-normalised, returned transposed [E, T].  (The reference adds ALL text rows at :25, which only broadcasts when

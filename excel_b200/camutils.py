@@ -10,6 +10,7 @@ def cure_attr_map(model, inputs, ex_feats):
         return model(inputs, ex_feats=ex_feats)
 
 
+@_lib.on_tensor_device
 def merge_flipped_maps(attr_2b, b, gh, gw):
     """utils/camutils.py:19-26: element-max of the maps of x and flip(x) (un-flipped), per-(b,c) min subtracted,
     divided by (max + 1e-5).  attr_2b [2b, n_p, K] -> [b, n_p, K]."""
@@ -45,6 +46,7 @@ def get_mask_by_radius(h=20, w=20, radius=8, device="cuda"):
     return mask
 
 
+@_lib.on_tensor_device
 def cams_to_affinity_label(cam_label, mask=None, ignore_index=255):
     """utils/camutils.py:438-457: cam_label [b,h,w] -> [b, (h//16)*(w//16), (h//16)*(w//16)] int64."""
     b, h, w = cam_label.shape
@@ -59,6 +61,7 @@ def cams_to_affinity_label(cam_label, mask=None, ignore_index=255):
     return out
 
 
+@_lib.on_tensor_device
 def lam_to_label(cam, cls_label, img_box=None, bkg_thre=0.5, high_thre=None, low_thre=None, ignore_mid=False, ignore_index=None):
     """utils/camutils.py:123-143: (valid_cam [b,c,h,w], pseudo_label [b,h,w] int64)."""
     b, c, h, w = cam.shape

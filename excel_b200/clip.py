@@ -5,6 +5,7 @@ import torch
 from . import _lib
 
 
+@_lib.on_tensor_device
 def clip_feature_surgery(image_features, text_features, redundant_feats=None, t=2):
     """clip/clip.py:288-310: image_features [B,N,E], text_features [T,E] -> [B,N,T] (detached)."""
     if redundant_feats is not None:
@@ -20,6 +21,7 @@ def clip_feature_surgery(image_features, text_features, redundant_feats=None, t=
     return out
 
 
+@_lib.on_tensor_device
 def token_normalize(tok):
     """clip/clip.py:353: tok / tok.norm(dim=1, keepdim=True) for tok [B,N,E]."""
     tok = _lib.f32c(tok)

@@ -1,5 +1,7 @@
 // Library-level entry points: error channel, version, device probe.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -15,7 +17,7 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static unsigned long long g_launches = 0;  // kernels enqueued by this library (single host thread per process)
+static std::atomic<unsigned long long> g_launches{0};  // kernels enqueued by this library
 
 int check_launch(const char* what) {
     ++g_launches;
@@ -28,7 +30,7 @@ int check_launch(const char* what) {
 
 extern "C" const char* excel_last_error(void) { return xl::g_err; }
 extern "C" int excel_version(void) { return 1; }
-extern "C" int64_t excel_launch_count(void) { return (int64_t)xl::g_launches; }
+extern "C" int64_t excel_launch_count(void) { return (int64_t)xl::g_launches.load(); }
 extern "C" int excel_device_arch(int device) {
     cudaDeviceProp p;
     if (cudaGetDeviceProperties(&p, device) != cudaSuccess) {

@@ -216,7 +216,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const uint64_t b_hi = umma_desc_sw128(vbox), b_lo = umma_desc_sw128(vbox + kTile);
                     const uint32_t d = tmem_o + (uint32_t)(qp.hh * 64);
                     const uint32_t first = (qp.kb | qp.half) != 0;
-                    if (leader && !(p.dbg & 1)) {
+                    if (leader) {
                         // keys 16k..16k+15 of the sub-tile live in its columns 16k..16k+15: hi pairs in +0..7, lo pairs in +8..15
                         if (nvalid > 48) {
 #pragma unroll
@@ -282,7 +282,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         constexpr bool TAIL = decltype(tail_tag)::value;
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            if ((TAIL && key0 + c * 16 >= p.N) || (p.dbg & 2)) break;   // (uniform) padding keys only: columns unused
+                            if (TAIL && key0 + c * 16 >= p.N) break;   // (uniform) padding keys only: columns unused
                             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + cq * 32 + c * 16);
                             uint32_t r[16];
                             tmem_ld16(taddr, r);
@@ -324,7 +324,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
                     // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
                     // a reduce-add (performed in L2) for the others -- no thread waits on global memory.
-                    if (nrow > 0 && !(p.dbg & 4)) {
+                    if (nrow > 0) {
                         const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
@@ -414,10 +414,9 @@ int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows,
 }
 
 int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_once = 0;
+    if (first_use_on_device(attr_once)) {
         XL_CUDA(cudaFuncSetAttribute(attn_pv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPvSmem));
-        attr_set = true;
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.D == p.H * 64, "attn_pv: bad shape");
     XL_REQUIRE(p.ml && p.out && p.o, "attn_pv: missing buffers");

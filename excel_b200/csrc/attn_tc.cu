@@ -341,11 +341,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, cudaStream_t st, bool stats_only) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_once = 0;
+    if (first_use_on_device(attr_once)) {
         XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
         XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
-        attr_set = true;
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.ntypes >= 1 && p.ntypes <= 3, "attn_scores: bad shape");
     XL_REQUIRE(p.m && (p.out || stats_only), "attn_scores: missing buffers");

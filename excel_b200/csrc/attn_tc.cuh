@@ -34,7 +34,6 @@ struct AttnPvParams {
     float* out;             // [B,N,Npad] scratch, Npad = round_up(N,4): coef * sum_h P[b,h], written by TMA store / reduce-add
     float coef;
     __half* o;              // split-fp16 [B*N, 2*D] (hi | lo): O[b, :, h*64..] = P[b,h] V[b,h]
-    int dbg;                // timing experiments only (EXCEL_PV_DBG): 1 no PV MMAs, 2 no epilogue math, 4 no map flush
 };
 // tmQ: split qkv [B*N, 6D], box 64 x 128 rows (V is consumed in place as an MN-major B operand: no transpose)
 int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st);

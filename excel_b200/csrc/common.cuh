@@ -32,6 +32,16 @@ int sgemm2(const float* A, const float* B, float* C, const float* bias, const fl
            int64_t lda, int64_t ldb, int64_t ldc, int batch, int64_t sA, int64_t sB, int64_t sC, int nb2, int64_t sA2,
            int64_t sB2, int64_t sC2, float alpha, int b_is_nk, int act, cudaStream_t st);
 
+// Function attributes (cudaFuncSetAttribute) are per DEVICE: `once` holds one bit per device ordinal; returns true the first
+// time it is called with a given device current (single host thread per process).
+inline bool first_use_on_device(unsigned long long& once) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;   // unknown: (re)apply the attribute
+    if (once & (1ull << dev)) return false;
+    once |= 1ull << dev;
+    return true;
+}
+
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

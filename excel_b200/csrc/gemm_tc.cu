@@ -402,8 +402,8 @@ int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
 }
 
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_once = 0;
+    if (first_use_on_device(attr_once)) {
 #define XL_TC_ATTR(BN_) \
         XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(BN_))); \
         XL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN_, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(BN_))); \
@@ -412,7 +412,6 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
         XL_TC_ATTR(128);
         XL_TC_ATTR(64);
 #undef XL_TC_ATTR
-        attr_set = true;
     }
     XL_REQUIRE(p.M > 0 && p.N > 0 && p.kblocks > 0 && batch > 0 && p.nb2 >= 1 && batch % p.nb2 == 0,
                "tc_gemm: bad shape M=%d N=%d kblocks=%d batch=%d", p.M, p.N, p.kblocks, batch);

@@ -10,7 +10,6 @@
 // surgery blocks update feats[l-1] / feats[first-1] in place exactly where the reference's in-place `+=`
 // mutates the views it had already appended.
 #include <cuda_fp16.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "excel_b200.h"
@@ -173,8 +172,7 @@ static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, in
     p.M = (int)c.BN; p.N = Nout; p.kblocks = K / 64; p.a_lo_off = K; p.b_lo_off = K; p.nb2 = 1;
     p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f; p.act = act;
     p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
-    static const int force_bn = getenv("EXCEL_GEMM_BN") ? atoi(getenv("EXCEL_GEMM_BN")) : 0;   // tuning experiments only
-    const int bn = force_bn ? force_bn : (Nout % 256 == 0 ? 256 : 128);
+    const int bn = Nout % 256 == 0 ? 256 : 128;
     return tc_gemm(ma, mw, p, 1, bn, c.st);
 }
 
@@ -198,8 +196,6 @@ static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
     AttnPvParams q = {};
     q.B = c.B; q.H = c.H; q.N = c.N; q.D = c.D; q.xo = 0; q.yo = c.D; q.vo = 2 * c.D; q.lo_off = 3 * c.D;
     q.alpha = scale * 1.4426950408889634f; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
-    static const int dbg = getenv("EXCEL_PV_DBG") ? atoi(getenv("EXCEL_PV_DBG")) : 0;   // timing experiments only
-    q.dbg = dbg;
     if (int e = attn_pv(c.m.qkv_a, q, c.st)) return e;
     return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);   // API layout [B,N,N]
 }

@@ -36,6 +36,7 @@ def _p(t):
     return _lib.f32c(t)
 
 
+@_lib.on_tensor_device
 def segformer_head_tokens(head, feats):
     """head: the reference's SegFormerHead module (weights read in place); feats [L, M, C] token-major rows (any M).
     Returns the fused features [M, E] (row m = the 1x1-fused embedding of token m)."""
@@ -52,6 +53,7 @@ def segformer_head_tokens(head, feats):
     return _gemm(cat, wf, _p(head.linear_fuse.bias))                                            # 1x1 conv (:75)
 
 
+@_lib.on_tensor_device
 def segformer_head(head, x_all):
     """Drop-in for SegFormerHead.forward: x_all [L, B, C, h, w] (channel-major, as model_excel.py:60-63 builds it)
     -> [B, E, h, w]."""
@@ -61,6 +63,7 @@ def segformer_head(head, x_all):
     return out.reshape(B, h * w, -1).permute(0, 2, 1).reshape(B, -1, h, w).contiguous()
 
 
+@_lib.on_tensor_device
 def attn_pred(attn_fts, beta=1.0, gamma=3.0):
     """model/model_excel.py:71-76: attn_fts [B,C,h,w] -> sigmoid((cos-sim - batch mean) * 3) [B, h*w, h*w]."""
     f = _lib.f32c(attn_fts)

@@ -108,11 +108,12 @@ class SurgeryViT:
             raise RuntimeError(f"SurgeryViT: expected [B,3,S,S] square images, got {tuple(img.shape)}")
         if S % self.patch:
             raise RuntimeError(f"SurgeryViT: image size {S} is not a multiple of the patch size {self.patch}")
-        if ex_feats is not None:
-            return self._forward(img, lvc_attention(ex_feats, (S // self.patch) ** 2))
-        if self.graph:
-            return self._forward_graph(img)
-        return self._forward(img)
+        with torch.cuda.device(self.device):   # launches, streams and function attributes on the engine's device
+            if ex_feats is not None:
+                return self._forward(img, lvc_attention(ex_feats, (S // self.patch) ** 2))
+            if self.graph:
+                return self._forward_graph(img)
+            return self._forward(img)
 
     def _forward_graph(self, img):
         key = tuple(img.shape)
@@ -120,37 +121,47 @@ class SurgeryViT:
         if g is None:
             static_in = torch.empty_like(img)
             static_in.copy_(img)
-            self._forward(static_in)                      # warm-up outside the capture (function attributes, workspace)
+            # The captured kernels have their workspace pointers baked in: the graph owns a DEDICATED workspace that lives as
+            # long as the graph does (the shared self._ws may be re-allocated by a later, larger eager call).
+            ws = self._alloc_ws(img.shape[0], img.shape[2])
+            self._forward(static_in, ws=ws)               # warm-up outside the capture (function attributes)
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.lib().excel_launch_count()
             with torch.cuda.graph(graph):
-                outs = self._forward(static_in)
-            g = self._graphs[key] = (graph, static_in, outs, _lib.lib().excel_launch_count() - n0)
-        graph, static_in, outs, nlaunch = g
+                outs = self._forward(static_in, ws=ws)
+            g = self._graphs[key] = (graph, static_in, outs, _lib.lib().excel_launch_count() - n0, ws)
+        graph, static_in, outs, nlaunch, _ws = g
         static_in.copy_(img)
         graph.replay()
         self.replayed_launches += nlaunch      # kernels launched by graph replays (the library's counter sees host launches only)
         return outs
 
-    def _forward(self, img, lvc_attn=None):
+    def _alloc_ws(self, B, S):
+        nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
+        return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)   # 512 B-aligned by the allocator
+
+    def _forward(self, img, lvc_attn=None, ws=None):
         B, C, S, S2 = img.shape
         N = (S // self.patch) ** 2 + 1
-        nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
-        if self._ws is None or self._ws.numel() * 4 < nbytes:
-            self._ws = None
-            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)   # 512 B-aligned by the allocator
+        if ws is None:   # eager calls share one grow-only workspace (never referenced by a captured graph)
+            nbytes = _lib.lib().excel_vit_workspace_bytes(B, S, self.patch, self.width, self.heads)
+            if self._ws is None or self._ws.numel() * 4 < nbytes:
+                self._ws = None
+                self._ws = self._alloc_ws(B, S)
+            ws = self._ws
         tokens = torch.empty((B, N, self.embed), dtype=torch.float32, device=self.device)
         attn = torch.empty((self.layers, B, N, N), dtype=torch.float32, device=self.device)
         feats = torch.empty((self.layers, B, N, self.width), dtype=torch.float32, device=self.device)
         _lib.call("excel_vit_forward", ctypes.byref(self._w), _lib.ptr(img), img.stride(0), img.stride(1), img.stride(2), B, S,
-                  _lib.ptr(self._ws), self._ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.ptr(lvc_attn),
+                  _lib.ptr(ws), ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.ptr(lvc_attn),
                   _lib.stream())
         return tokens, attn, feats
 
     __call__ = forward
 
 
+@_lib.on_tensor_device
 def lvc_attention(ex_feats, n_p=None, beta=1.0, gamma=3.0):
     """clip/clip_surgery_model.py:127-137: decoder features [B,C,h,w] -> ex_attn [B,n_p,n_p] (fp32, CUDA)."""
     f = _lib.f32c(ex_feats)
@@ -170,6 +181,7 @@ def lvc_attention(ex_feats, n_p=None, beta=1.0, gamma=3.0):
 
 
 _ENGINES = {}
+ENGINE_OPTS = {"graph": False}   # how engine_for builds its engines (install(graph=True): CUDA-graph replay, outputs reused per shape)
 
 
 def engine_for(model, n_surgery=5):
@@ -181,7 +193,9 @@ def engine_for(model, n_surgery=5):
     ver = tuple((p.data_ptr(), p._version) for p in visual.parameters())
     hit = _ENGINES.get(key)
     if hit is None or hit[0] != ver:
-        _ENGINES[key] = (ver, SurgeryViT.from_visual(visual, n_surgery))
+        dev = next(visual.parameters()).device
+        _ENGINES[key] = (ver, SurgeryViT(pack_from_visual(visual), n_surgery, device=dev if dev.type == "cuda" else "cuda",
+                                         graph=ENGINE_OPTS["graph"]))
     return _ENGINES[key][1]
 
 

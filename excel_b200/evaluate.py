@@ -5,6 +5,7 @@ import torch
 from . import _lib
 
 
+@_lib.on_tensor_device
 def confusion_hist(label_true, label_pred, num_classes, hist=None):
     """Accumulate utils/evaluate.py:_fast_hist on the device.  int64 CUDA tensors of equal numel;
     returns / updates hist [num_classes, num_classes] int64."""

@@ -13,8 +13,20 @@ import os
 import sys
 
 
-def install(reference_root=None):
-    """Patch the reference modules in place.  Returns the dict {qualified name: original object}."""
+def install(reference_root=None, graph=False):
+    """Patch the reference modules in place.  Returns the dict {qualified name: original object}.
+
+    graph=True: the encoder engines built for the reference's CLIP modules replay their ~190 launches as one CUDA graph
+    per input shape (no host launch gaps -- what the batch-1 loops of tools/infer_lam.py / engine/validatation_engine.py
+    need).  The three tensors a forward returns are then REUSED by the next forward of the same shape: fine for those
+    loops (each image's outputs are consumed before the next `model(inputs)`), not for callers that keep them.
+
+    Behavioural differences to the reference after install() (also in INTEGRATION.md): `get_mask_by_radius` returns a CUDA
+    fp32 tensor (the reference: numpy float64; `cams_to_affinity_label` accepts both), `attr2cls_embedings` adds the
+    foreground text rows (the reference adds all rows, which only broadcasts when there are no background rows), and no
+    patched function has a CPU path: CPU tensors raise."""
+    from . import encoder as _enc
+    _enc.ENGINE_OPTS["graph"] = bool(graph)
     if reference_root:
         reference_root = os.path.abspath(reference_root)
         if reference_root not in sys.path:

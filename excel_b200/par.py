@@ -27,6 +27,7 @@ def _side_streams(dev, n):
     return pool[:n]
 
 
+@_lib.on_tensor_device
 def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2, segments=None):
     """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
     segments: optional [(b0, b1, max planes per image)] runs of consecutive images launched separately (so that each
@@ -68,6 +69,7 @@ def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group
     return out
 
 
+@_lib.on_tensor_device
 def par_affinity(imgs, size, dilations, w1=W1, w2=W2):
     """utils/PAR.py:67-86 only: imgs [B,3,hi,wi] -> aff [B,8*n_dil,H,W]."""
     imgs = imgs.float()
@@ -83,6 +85,7 @@ def par_affinity(imgs, size, dilations, w1=W1, w2=W2):
     return aff[..., :W]
 
 
+@_lib.on_tensor_device
 def par_labels(planes, plane_off, plane_key, B):
     """utils/affutils.py:86-87: labels [B,H,W] int64 = plane_key[argmax over image b's planes]."""
     P, H, W = planes.shape

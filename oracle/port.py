@@ -429,20 +429,22 @@ def hot_path(W, text_attr_t, imgs, cls_labels, num_fg, caa_thre=0.79, num_iter=2
              out_hw=None, use_cv2=True):
     """tools/infer_lam.py:74-94 (training-free branch) for a batch: encoder -> CAM -> per image SVC -> PAR.
     text_attr_t [T,E] (= model.text_attr.permute(1,0)); cls_labels [B,num_fg] one-hot.
-    Returns dict(attr_maps_raw, attn_weights, labels list, cams list)."""
+    Returns dict(attr_maps_raw, attn_weights, all_feats, labels list, cams list (PAR input planes), refined list (PAR
+    output planes))."""
     tok, attn, feats = generate_clip_fts(W, imgs)
     attr = clip_feature_surgery(tok, text_attr_t)[:, 1:, :num_fg]               # model/model_excel.py:58
     par_imgs = imgs if par_imgs is None else par_imgs
     out_hw = tuple(imgs.shape[-2:]) if out_hw is None else out_hw
-    labels, cams = [], []
+    labels, cams, refined = [], [], []
     for i in range(imgs.shape[0]):
         cam_list, cls_lst = refine_cams_with_aff(attr[i], attn[:, i], cls_labels[i], imgs.shape[-2:],
                                                  caa_thre=caa_thre, use_cv2=use_cv2)
-        lab, cam, _ = refine_cams_with_bkg_weclip(cam_list, par_imgs[i], cls_lst, out_hw,
-                                                  num_iter=num_iter, use_cv2=use_cv2)
+        lab, cam, ref = refine_cams_with_bkg_weclip(cam_list, par_imgs[i], cls_lst, out_hw,
+                                                    num_iter=num_iter, use_cv2=use_cv2)
         labels.append(lab)
         cams.append(cam)
-    return dict(attr_maps_raw=attr, attn_weights=attn, all_feats=feats, labels=labels, cams=cams)
+        refined.append(ref)
+    return dict(attr_maps_raw=attr, attn_weights=attn, all_feats=feats, labels=labels, cams=cams, refined=refined)
 
 
 def fast_hist(label_true, label_pred, num_classes):

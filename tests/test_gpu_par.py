@@ -3,6 +3,7 @@ fixtures frozen from the reference (utils/PAR.py)."""
 import pytest
 import torch
 
+from _parity import label_parity
 from excel_b200 import synth
 from oracle import port
 
@@ -10,12 +11,7 @@ pytestmark = pytest.mark.gpu
 t = torch.from_numpy
 
 
-def _near_tie_mismatches(ref_planes, lab_ref, lab_gpu, tol=1e-5):
-    """label mismatches that are NOT explained by a top-2 margin below tol in the oracle."""
-    top2 = ref_planes.topk(2, dim=0).values
-    margin = (top2[0] - top2[1]) / top2[0].abs().clamp_min(1e-12)
-    bad = (lab_ref != lab_gpu)
-    return int((bad & (margin > tol)).sum()), int(bad.sum())
+_near_tie_mismatches = label_parity   # (hard, total): the one label gate, margin 1e-5 (tests/_parity.py)
 
 
 def test_par_golden(golden):

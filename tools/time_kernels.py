@@ -16,4 +16,4 @@ a.record()
 for _ in range(5):
     enc(imgs)
 b.record(); torch.cuda.synchronize()
-print("encoder ms", a.elapsed_time(b) / 5, "dbg", os.environ.get("EXCEL_PV_DBG"))
+print("encoder ms", a.elapsed_time(b) / 5)
