@@ -24,19 +24,20 @@ SIGNATURES = {
     "excel_confusion_hist": ([_p, _p, _i64, _i, _p, _p], _i),
     "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
     "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
-    "excel_svc_mean_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),
-    "excel_svc_seg_attention": ([_p, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p], _i),
+    "excel_svc_mean_attention": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),
+    "excel_svc_seg_attention": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "excel_svc_sinkhorn": ([_p, _i, _i, _i, _p, _p, _p], _i),
     "excel_svc_build_trans": ([_p, _p, _p, _i, _i, _p, _p], _i),
     "excel_svc_box_mask": ([_p, _i64, _i64, _p, _p, _i, _i, _i, _c.c_double, _p, _p, _p], _i),
     "excel_svc_propagate": ([_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p], _i),
     "excel_svc_cams_to_planes": ([_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p], _i),
     "excel_token_normalize": ([_p, _i, _i, _i, _p, _p, _p], _i),
-    "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _p, _p], _i),
+    "excel_cam_workspace_bytes": ([_i, _i, _i, _i], _i64),
+    "excel_cam_surgery": ([_p, _p, _i, _i, _i, _i, _p, _i64, _p, _p], _i),
     "excel_flip_merge": ([_p, _i, _i, _i, _i, _p, _p], _i),
     "excel_vit_workspace_bytes": ([_i, _i, _i, _i, _i], _i64),
-    "excel_split_f16": ([_p, _i64, _i, _i, _i, _p, _p], _i),
-    "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p, _p, _p], _i),
+    "excel_split_f16": ([_p, _i64, _i, _i, _i, _f, _p, _p], _i),
+    "excel_vit_forward": ([_p, _p, _i64, _i64, _i64, _i, _i, _p, _i64, _p, _p, _i64, _p, _p, _p], _i),
     "excel_lvc_attention": ([_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p], _i),
     "excel_attn_pred": ([_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p], _i),
     "excel_row_softmax": ([_p, _i, _i, _p, _p], _i),
@@ -52,14 +53,15 @@ SIGNATURES = {
 
 class VitLayer(ctypes.Structure):
     _fields_ = [(n, _p) for n in ("ln1_w", "ln1_b", "in_w", "in_b", "out_w", "out_b", "ln2_w", "ln2_b", "fc_w", "fc_b",
-                                  "proj_w", "proj_b", "in_ws", "out_ws", "fc_ws", "proj_ws")]
+                                  "proj_w", "proj_b", "in_ws", "out_ws", "fc_ws", "proj_ws")] + \
+               [(n, _f) for n in ("in_scale", "out_scale", "fc_scale", "proj_scale")]
 
 
 class VitWeights(ctypes.Structure):
     _fields_ = [(n, _i) for n in ("layers", "width", "heads", "patch", "embed", "grid0", "n_surgery")] + \
                [(n, _p) for n in ("conv1", "cls", "pos", "ln_pre_w", "ln_pre_b", "ln_post_w", "ln_post_b", "proj", "conv1_s",
                                   "proj_t_s")] + \
-               [("blocks", ctypes.POINTER(VitLayer))]
+               [("conv1_scale", _f), ("proj_t_scale", _f), ("blocks", ctypes.POINTER(VitLayer))]
 
 
 _lib = None

@@ -24,7 +24,8 @@ def _class_lists(cls_labels):
 
 
 def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None, seg_attn=None):
-    """attr_maps [B,n_p,K]; attn [L,B,N,N] (arbitrary stride_l / stride_b, rows contiguous).
+    """attr_maps [B,n_p,K]; attn [L,B,N,N] (arbitrary layer / image / row strides, columns contiguous: the encoder returns a
+    view with row pitch round_up(N,4)).
     Returns refined [Q, n_p] for the Q = sum_b n_b (image, class) pairs, image-major (images in `order`, default
     0..B-1), classes ascending."""
     dev = attr_maps.device
@@ -32,7 +33,7 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, orde
     L, _, N, _ = attn.shape
     if N - 1 != n_p or gh * gw != n_p:
         raise RuntimeError(f"SVC: attention has {N - 1} patches, CAM has {n_p}, grid {gh}x{gw}")
-    if attn.stride(3) != 1 or attn.stride(2) != N:
+    if attn.stride(3) != 1 or attn.stride(2) < N:
         attn = attn.contiguous()
     attr_maps = _f32(attr_maps)
     if attr_maps.stride(2) != 1:
@@ -45,12 +46,12 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, orde
     st = _lib.stream()
     A = torch.empty((B, n_p, n_p), dtype=torch.float32, device=dev)
     if seg_attn is None:
-        _lib.call("excel_svc_mean_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), L, B, N, attn_layers,
+        _lib.call("excel_svc_mean_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), attn.stride(2), L, B, N, attn_layers,
                   _lib.ptr(A), st)
     else:   # LVC branch (utils/affutils.py:182-195): seg_attn [B, n_p, n_p]
         seg = _lib.f32c(seg_attn).reshape(B, n_p, n_p)
         dws = torch.empty((B * attn_layers,), dtype=torch.float32, device=dev)
-        _lib.call("excel_svc_seg_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), L, B, N, attn_layers,
+        _lib.call("excel_svc_seg_attention", _lib.ptr(attn), attn.stride(0), attn.stride(1), attn.stride(2), L, B, N, attn_layers,
                   _lib.ptr(seg), _lib.ptr(dws), _lib.ptr(A), st)
     r = torch.empty((B, n_p), dtype=torch.float32, device=dev)
     c = torch.empty_like(r)

@@ -1,7 +1,9 @@
 """Attribute-bank utilities -- drop-ins for the reference's ``utils/attrutils.py`` on sm_100a.
 
-``attrmap2clsmap`` and ``attr2cls_embedings`` are plain dense contractions; they run on ``excel_sgemm`` (exact fp32)
-with a row-softmax kernel in between.  ``load_text_attri`` is file I/O and stays PyTorch.
+``attrmap2clsmap`` (patch x attribute-bank maps against the class flags, the per-batch contraction) runs on the tcgen05
+GEMM engine (``excel_gemm_tc``: TMA-fed split-fp16 operands, fp32 accumulation in TMEM); ``attr2cls_embedings`` is
+init-time work on a [cls, A] matrix and runs on ``excel_sgemm`` (exact fp32) with a row-softmax kernel in between.
+``load_text_attri`` is file I/O and stays PyTorch.
 """
 import os
 
@@ -35,7 +37,16 @@ def load_text_attri(pt_path):
 def attrmap2clsmap(attri_flag, attr_maps):
     """utils/attrutils.py:11-17: attr_maps [B,n_p,A] @ attri_flag[cls,A]^T -> [B,n_p,cls]."""
     B, n_p, A = attr_maps.shape
-    out = _sgemm(attr_maps.reshape(B * n_p, A), attri_flag.to(torch.float32), b_is_nk=True)
+    X = _lib.f32c(attr_maps).reshape(B * n_p, A)
+    Fl = _lib.f32c(attri_flag)
+    if Fl.shape[1] != A:
+        raise RuntimeError(f"attrutils: inner dimensions differ ({tuple(attr_maps.shape)} x {tuple(attri_flag.shape)})")
+    M, N = X.shape[0], Fl.shape[0]
+    kp = (A + 63) // 64 * 64
+    out = torch.empty((M, N), dtype=torch.float32, device=X.device)
+    ws = torch.empty((4 * (M + N) * kp,), dtype=torch.uint8, device=X.device)
+    _lib.call("excel_gemm_tc", _lib.ptr(X), _lib.ptr(Fl), _lib.ptr(out), None, None, M, N, A, A, A, N, 1.0, 0, _lib.ptr(ws),
+              ws.numel(), _lib.stream())
     return out.view(B, n_p, -1)
 
 

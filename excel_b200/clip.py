@@ -15,9 +15,10 @@ def clip_feature_surgery(image_features, text_features, redundant_feats=None, t=
     B, N, E = F.shape
     if T.shape[1] != E:
         raise RuntimeError(f"clip_feature_surgery: feature dim {E} vs text dim {T.shape[1]}")
-    S = torch.empty((B, N, T.shape[0]), dtype=torch.float32, device=F.device)
-    out = torch.empty_like(S)
-    _lib.call("excel_cam_surgery", _lib.ptr(F), _lib.ptr(T), B, N, E, T.shape[0], _lib.ptr(S), _lib.ptr(out), _lib.stream())
+    out = torch.empty((B, N, T.shape[0]), dtype=torch.float32, device=F.device)
+    nbytes = _lib.lib().excel_cam_workspace_bytes(B, N, E, T.shape[0])
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=F.device)      # split operands + S + min/max partials
+    _lib.call("excel_cam_surgery", _lib.ptr(F), _lib.ptr(T), B, N, E, T.shape[0], _lib.ptr(ws), nbytes, _lib.ptr(out), _lib.stream())
     return out
 
 

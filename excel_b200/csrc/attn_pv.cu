@@ -18,7 +18,8 @@
 // polled independently), MMA issuer (S runs up to four sub-steps ahead of P V), 16 epilogue warps in two groups that
 // ping-pong over the key halves.  The head-reduced map leaves once per (head group, key block) through the warp's staging
 // block and TMA: a plain store for the first head group, a reduce-add in L2 for the others (fixed order per address, so
-// the result is bit-reproducible), into a row-padded scratch [B,N,Npad] that attn_compact_kernel rewrites to [B,N,N].
+// the result is bit-reproducible), straight into the API's attention tensor, whose rows are padded to Npad = round_up(N,4)
+// floats (TMA needs 16 B-aligned row pitches; the Python side returns the [.., :N] view).
 // Key blocks are trimmed to the valid keys rounded up to 16 (N = 1025: the ninth block is one 16-wide MMA).
 #include <cuda_fp16.h>
 
@@ -33,7 +34,7 @@ namespace xl {
 
 namespace {
 
-constexpr int kHG = 4;                          // heads per group (O accumulators: kHG x 64 TMEM columns)
+constexpr int kHG = 4;                          // max heads per group (O accumulators: kHG x 64 TMEM columns); p.hpi <= kHG
 constexpr uint32_t kTile = 128 * 64 * 2;        // 16 KB: 128 rows x 64 halves (one SWIZZLE_128B operand tile)
 constexpr uint32_t kXYStage = 4 * kTile;        // X_hi, X_lo, Y_hi, Y_lo
 constexpr uint32_t kVStage = 2 * kTile;         // V_hi, V_lo: 128 keys x 64 head-dim channels, straight from the qkv matrix
@@ -69,8 +70,13 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.N + 127) / 128;
-    const int ngrp = (p.H + kHG - 1) / kHG;
-    const int items = p.B * nblk;
+    const int hpi = p.hpi;                                  // heads per group (1, 2 or 4)
+    const int ngrp = (p.H + hpi - 1) / hpi;
+    // Work item = (image, 128-row query block) walking all head groups, or -- p.gsplit, small batches -- one (image, query
+    // block, head group) each, so that B * nblk * ngrp CTAs share the chip; a split item writes its partial head-sum into
+    // slice g of the scratch map [ngrp][B,N,Npad] with plain stores (attn_combine_kernel adds the slices in a fixed order).
+    const int gs = p.gsplit ? ngrp : 1;
+    const int items = p.B * nblk * gs;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXYStages; ++s) { mbar_init(&xy_full[s], 1); mbar_init(&xy_empty[s], 1); }
@@ -105,22 +111,22 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             struct It { int item, g, kb, hh; };
             auto advance = [&](It& it) {
-                const int hc = min(kHG, p.H - it.g * kHG);
+                const int hc = min(hpi, p.H - it.g * hpi);
                 if (++it.hh < hc) return;
                 it.hh = 0;
                 if (++it.kb < nblk) return;
                 it.kb = 0;
-                if (++it.g < ngrp) return;
-                it.g = 0;
+                if (!p.gsplit && ++it.g < ngrp) return;
                 it.item += gridDim.x;
+                it.g = p.gsplit ? it.item % gs : 0;
             };
-            It ix = {(int)blockIdx.x, 0, 0, 0}, iv = ix;
+            It ix = {(int)blockIdx.x, p.gsplit ? (int)blockIdx.x % gs : 0, 0, 0}, iv = ix;
             uint32_t nx = 0, nv = 0;
             while (ix.item < items || iv.item < items) {
                 if (ix.item < items) {
                     const int s = nx % kXYStages;
                     if (mbar_try(&xy_empty[s], ((nx / kXYStages) & 1) ^ 1)) {
-                        const int rb = ix.item % nblk, b = ix.item / nblk, h = ix.g * kHG + ix.hh;
+                        const int rb = (ix.item / gs) % nblk, b = ix.item / (gs * nblk), h = ix.g * hpi + ix.hh;
                         uint8_t* st = xy + s * kXYStage;
                         const int xr = b * p.N + rb * 128, yr = b * p.N + ix.kb * 128;
                         const int xc = p.xo + h * 64, yc = p.yo + h * 64;
@@ -138,7 +144,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (iv.item < items) {
                     const int sv = nv % kVStages;
                     if (mbar_try(&v_empty[sv], ((nv / kVStages) & 1) ^ 1)) {
-                        const int b = iv.item / nblk, h = iv.g * kHG + iv.hh;
+                        const int b = iv.item / (gs * nblk), h = iv.g * hpi + iv.hh;
                         uint8_t* vt = vs + sv * kVStage;
                         const int vr = b * p.N + iv.kb * 128, vc = p.vo + h * 64;   // V rows = keys, columns = head-dim channels
                         if (leader) {
@@ -163,8 +169,9 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t ngd = 0;
         const uint32_t xy0 = smem_u32(xy), vs0 = smem_u32(vs);
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            for (int g = 0; g < ngrp; ++g) {
-                const int hc = min(kHG, p.H - g * kHG);
+            const int g_lo = p.gsplit ? item % gs : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
+            for (int g = g_lo; g < g_hi; ++g) {
+                const int hc = min(hpi, p.H - g * hpi);
                 const int U = ((nblk - 1) * 2 + nsub_last) * hc;
                 auto next = [&](Sub& q) {     // sub-step order: key block, head, 64-key half
                     const int nsub = q.kb < nblk - 1 ? 2 : nsub_last;
@@ -254,13 +261,15 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float* stg = reinterpret_cast<float*>(stg_base) + ew * 512;   // warp-private 32 rows x 16 floats
         uint32_t gl = 0, ngd = 0;                                      // load steps seen: this group's sub-tile is 2 * gl + grp
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int rb = item % nblk, b = item / nblk;
+            const int rb = (item / gs) % nblk, b = item / (gs * nblk);
             const int row = rb * 128 + trow;
             const bool row_ok = row < p.N;
             const int nrow = min(32, p.N - rb * 128 - lg * 32);       // valid rows of this warp's 32 (may be <= 0)
-            for (int g = 0; g < ngrp; ++g) {
-                const int hc = min(kHG, p.H - g * kHG);
-                const float* mrow = p.ml + ((int64_t)b * p.H + g * kHG) * p.N + row;   // + hh * N
+            const int g_lo = p.gsplit ? item % gs : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
+            for (int g = g_lo; g < g_hi; ++g) {
+                const int hc = min(hpi, p.H - g * hpi);
+                const int zo = p.gsplit ? g * p.B + b : b;            // map slice of this item
+                const float* mrow = p.ml + ((int64_t)b * p.H + g * hpi) * p.N + row;   // + hh * N
                 for (int kb = 0; kb < nblk; ++kb) {
                     const int key0 = kb * 128 + grp * 64 + cq * 32;   // this warp's 32 keys of the key block
                     float acc[2][16];
@@ -339,8 +348,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                if (g == 0) tma_store_3d(&tmO, stg, kc, rb * 128 + lg * 32, b);
-                                else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, b);
+                                if (g == 0 || p.gsplit) tma_store_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
+                                else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
                                 tma_store_commit();
                             }
                         }
@@ -356,7 +365,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         uint32_t r[16];
                         tmem_ld16(tmem_o + lane_addr + (uint32_t)(qt * 64 + q * 16), r);
                         if (row_ok) {
-                            __half* oh = p.o + ((int64_t)b * p.N + row) * (2 * p.D) + (g * kHG + qt) * 64 + q * 16;
+                            __half* oh = p.o + ((int64_t)b * p.N + row) * (2 * p.D) + (g * hpi + qt) * 64 + q * 16;
 #pragma unroll
                             for (int j = 0; j < 2; ++j) {
                                 __align__(16) __half2 h2[4], l2[4];
@@ -389,28 +398,17 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 }
 
-// dense [rows, N] <- row-padded [rows, Npad]: one aligned 16 B load per thread, four coalesced scalar stores
+// out[i] = sum_g part[g][i] in the fixed order g = 0, 1, ... (split launches: one partial head-sum map per head group)
 __global__ void __launch_bounds__(256)
-attn_compact_kernel(const float* __restrict__ src, int Npad, float* __restrict__ dst, int N, int64_t total4) {
-    const int n4 = Npad >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = i / n4;
-        const int c = (int)(i - row * n4) * 4;
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(src + row * Npad + c));
-        float* o = dst + row * N + c;
-        o[0] = v.x;
-        if (c + 1 < N) o[1] = v.y;
-        if (c + 2 < N) o[2] = v.z;
-        if (c + 3 < N) o[3] = v.w;
+attn_combine_kernel(const float4* __restrict__ part, int ngrp, int64_t slice4, float4* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slice4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 a = __ldcs(part + i);
+        for (int g = 1; g < ngrp; ++g) {
+            const float4 v = __ldcs(part + g * slice4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        out[i] = a;
     }
-}
-
-int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st) {
-    XL_REQUIRE(Npad % 4 == 0 && Npad >= N && Npad - N < 4, "attn_compact: bad padding");
-    const int64_t total4 = rows * (Npad >> 2);
-    const int64_t blocks = ceil_div64(total4, 256 * 4);
-    attn_compact_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(padded, Npad, out, N, total4);
-    return check_launch("attn_compact_kernel");
 }
 
 int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st) {
@@ -420,11 +418,34 @@ int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st) {
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.D == p.H * 64, "attn_pv: bad shape");
     XL_REQUIRE(p.ml && p.out && p.o, "attn_pv: missing buffers");
+    XL_REQUIRE(p.hpi == 1 || p.hpi == 2 || p.hpi == 4, "attn_pv: heads per group must be 1, 2 or 4");
+    const int ngrp = (p.H + p.hpi - 1) / p.hpi, nblk = (p.N + 127) / 128, Npad = (p.N + 3) & ~3;
+    XL_REQUIRE(!p.gsplit || p.part, "attn_pv: split launches need the partial-map scratch");
     CUtensorMap tmO;
-    if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
-    const int items = p.B * ((p.N + 127) / 128);
+    if (int e = make_map_store(&tmO, p.gsplit ? p.part : p.out, p.gsplit ? p.B * ngrp : p.B, p.N)) return e;
+    const int items = p.B * nblk * (p.gsplit ? ngrp : 1);
     attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmO, p);
-    return check_launch("attn_pv_kernel");
+    if (int e = check_launch("attn_pv_kernel")) return e;
+    if (!p.gsplit) return 0;
+    const int64_t slice4 = (int64_t)p.B * p.N * Npad / 4;
+    const int64_t blocks = ceil_div64(slice4, 256 * 2);
+    attn_combine_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(p.part), ngrp, slice4, reinterpret_cast<float4*>(p.out));
+    return check_launch("attn_combine_kernel");
+}
+
+// heads per group / split decision for a batch: keep the whole-item form (3 head groups of 4 walked by one CTA, the map
+// reduced in L2 in a fixed order) while (image, query block) items fill the chip; below that one item per head group, with
+// as few heads per group as it takes to reach one CTA per SM.
+void attn_pv_plan(int B, int H, int N, int* hpi, int* gsplit) {
+    const int nblk = (N + 127) / 128;
+    *hpi = 4; *gsplit = 0;
+    if (B * nblk >= (kNumSMs * 3) / 4) return;
+    *gsplit = 1;
+    for (int h = 4; h >= 1; h /= 2) {
+        *hpi = h;
+        if (B * nblk * ((H + h - 1) / h) >= kNumSMs) break;
+    }
 }
 
 }  // namespace xl

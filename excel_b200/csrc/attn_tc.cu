@@ -308,7 +308,39 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 // head-reduced map block [32 rows x 32 keys] of this warp: two 16-column halves through the warp's staging
                 // block (SWIZZLE_64B rows) and out by TMA store (clipped at the row / padded-column extents of the map)
                 const int key0 = kb * 128 + qt * 32;
-                if (key0 < p.N && rb * 128 + lg * 32 < p.N) {
+                if (p.out_split) {
+                    // ... or straight into the split-fp16 A operand of the new-path P V GEMM (no fp32 map, no split pass):
+                    // 2^10 p = hi + lo, [32 rows x 16 keys] halves each (32 B rows), columns [0, np) hi | [np, 2 np) lo; the
+                    // padding keys N .. np-1 are written as zeros (K padding of the GEMM).
+                    if (key0 < p.np && rb * 128 + lg * 32 < p.N) {
+                        uint8_t* wb = reinterpret_cast<uint8_t*>(wbuf);
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            if (lane == 0) tma_store_wait_read<0>();
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                __align__(16) __half2 h2[4], l2[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float v0 = p.coef * acc[hf * 16 + 8 * q + 2 * e], v1 = p.coef * acc[hf * 16 + 8 * q + 2 * e + 1];
+                                    h2[e] = __floats2half2_rn(v0, v1);
+                                    const float2 hf2 = __half22float2(h2[e]);
+                                    l2[e] = __floats2half2_rn(v0 - hf2.x, v1 - hf2.y);
+                                }
+                                *reinterpret_cast<uint4*>(wb + lane * 32 + q * 16) = *reinterpret_cast<const uint4*>(h2);
+                                *reinterpret_cast<uint4*>(wb + 1024 + lane * 32 + q * 16) = *reinterpret_cast<const uint4*>(l2);
+                            }
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_3d(&tmO, wb, key0 + hf * 16, rb * 128 + lg * 32, b);
+                                tma_store_3d(&tmO, wb + 1024, p.np + key0 + hf * 16, rb * 128 + lg * 32, b);
+                                tma_store_commit();
+                            }
+                        }
+                    }
+                } else if (key0 < p.N && rb * 128 + lg * 32 < p.N) {
                     const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -347,14 +379,21 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, cudaStream_t st, bo
         XL_CUDA(cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kASmem));
     }
     XL_REQUIRE(p.B > 0 && p.H > 0 && p.N > 0 && p.ntypes >= 1 && p.ntypes <= 3, "attn_scores: bad shape");
-    XL_REQUIRE(p.m && (p.out || stats_only), "attn_scores: missing buffers");
+    XL_REQUIRE(p.m && (p.out || p.out_split || stats_only), "attn_scores: missing buffers");
     const int nblk = (p.N + 127) / 128;
     const int items0 = p.B * p.ntypes * p.H * nblk, items1 = p.B * nblk * nblk;
     attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmQ, p);
     if (int e = check_launch("attn_tc_kernel<stats>")) return e;
     if (stats_only) return 0;
     CUtensorMap tmO;
-    if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
+    if (p.out_split) {
+        // split-fp16 map [B, N, 2 np] (hi | lo): 16-column x 32-row fp16 boxes (32 B rows, no swizzle)
+        XL_REQUIRE(p.np % 64 == 0 && p.np >= p.N, "attn_scores: bad split pitch");
+        const uint64_t dims[3] = {(uint64_t)2 * p.np, (uint64_t)p.N, (uint64_t)p.B};
+        const uint64_t strides[2] = {(uint64_t)2 * p.np * 2, (uint64_t)2 * p.np * 2 * p.N};
+        const uint32_t box[3] = {16, 32, 1};
+        if (int e = encode_tensor_map(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, p.out_split, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
+    } else if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
     attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmO, p);
     return check_launch("attn_tc_kernel<map>");
 }

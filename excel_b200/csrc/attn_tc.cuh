@@ -18,6 +18,8 @@ struct AttnParams {
     float* m;               // [ntypes,B,H,N] row statistic m + log2(l) - 10: written by the stats pass, read by the map pass
     float* out;             // row-padded map [B,N,Npad], Npad = round_up(N,4): coef * sum_types sum_h P[b,h]
     float coef;
+    __half* out_split;      // instead of `out`: the map x 2^10 as a split-fp16 GEMM operand [B*N, 2*np] (hi | lo), np = round_up(N,64)
+    int np;
 };
 
 // stats pass (always) + map pass (skipped with stats_only)
@@ -31,13 +33,15 @@ struct AttnPvParams {
     int lo_off;
     float alpha;            // scale * log2(e)
     const float* ml;        // [B,H,N]  m + log2(l) - 10
-    float* out;             // [B,N,Npad] scratch, Npad = round_up(N,4): coef * sum_h P[b,h], written by TMA store / reduce-add
+    float* out;             // [B,N,Npad], Npad = round_up(N,4): coef * sum_h P[b,h], written by TMA store / reduce-add
     float coef;
+    int hpi;                // heads per group (1, 2 or 4) and
+    int gsplit;             // 1: one work item per (image, query block, head group) -- small batches; the groups' partial maps go
+    float* part;            //    to part [ngrp][B,N,Npad] and are summed into `out` in a fixed order (attn_pv_plan chooses)
     __half* o;              // split-fp16 [B*N, 2*D] (hi | lo): O[b, :, h*64..] = P[b,h] V[b,h]
 };
 // tmQ: split qkv [B*N, 6D], box 64 x 128 rows (V is consumed in place as an MN-major B operand: no transpose)
 int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st);
-// dense [rows, N] <- padded [rows, Npad]
-int attn_compact(const float* padded, int Npad, float* out, int N, int64_t rows, cudaStream_t st);
+void attn_pv_plan(int B, int H, int N, int* hpi, int* gsplit);
 
 }  // namespace xl

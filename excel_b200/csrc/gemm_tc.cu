@@ -389,7 +389,7 @@ __global__ void split_f16_kernel(const float* __restrict__ x, int64_t ldx, int r
     const int r = blockIdx.y;
     if (c >= Kp) return;
     float v = c < cols ? x[(int64_t)r * ldx + c] * scale : 0.f;
-    const __half h = __float2half_rn(v);
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));   // hi saturates: |v| <= 2 x 65504 stays finite
     out[(int64_t)r * 2 * Kp + c] = h;
     out[(int64_t)r * 2 * Kp + Kp + c] = __float2half_rn(v - __half2float(h));
 }

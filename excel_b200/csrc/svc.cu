@@ -21,13 +21,13 @@ namespace xl {
 
 // ---- A[b] = mean_l attn[l0+l, b, 1:, 1:]  (affutils.py:180,197) ----------------------------------
 // attn: [L,B,N,N]; A: [B,n_p,n_p], n_p = N-1.  One thread per output element, x fastest.
-__global__ void svc_mean_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int N,
+__global__ void svc_mean_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int N,
                                 int l0, int nl, float* __restrict__ A) {
     const int np = N - 1;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y, b = blockIdx.z;
     if (j >= np) return;
-    const float* p = attn + (int64_t)l0 * stride_l + (int64_t)b * stride_b + (int64_t)(i + 1) * N + (j + 1);
+    const float* p = attn + (int64_t)l0 * stride_l + (int64_t)b * stride_b + (int64_t)(i + 1) * stride_r + (j + 1);
     float s = 0.f;
     for (int l = 0; l < nl; ++l) s += __ldcs(p + (int64_t)l * stride_l);
     A[((int64_t)b * np + i) * np + j] = s / (float)nl;
@@ -36,7 +36,7 @@ __global__ void svc_mean_kernel(const float* __restrict__ attn, int64_t stride_l
 // ---- seg_attn branch (affutils.py:182-195): keep the layers whose sum(seg_attn - A_l) is <= the mean over layers ----
 // d[b,l] = sum_ij (seg[b,i,j] - attn[l0+l, b, 1+i, 1+j]); one block per (l, b), fixed summation order
 __global__ void __launch_bounds__(1024)
-svc_layer_diff_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int N, int l0,
+svc_layer_diff_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int N, int l0,
                       const float* __restrict__ seg, float* __restrict__ d) {
     __shared__ float red[32];
     const int np = N - 1, l = blockIdx.x, b = blockIdx.y, nl = gridDim.x;
@@ -45,7 +45,7 @@ svc_layer_diff_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t 
     float acc = 0.f;
     for (int i = threadIdx.x >> 5; i < np; i += 32) {
         float r = 0.f;
-        for (int j = threadIdx.x & 31; j < np; j += 32) r += s[(int64_t)i * np + j] - a[(int64_t)(i + 1) * N + j + 1];
+        for (int j = threadIdx.x & 31; j < np; j += 32) r += s[(int64_t)i * np + j] - a[(int64_t)(i + 1) * stride_r + j + 1];
         acc += r;
     }
     acc = block_reduce(acc, red, OpSum(), 0.f);
@@ -53,7 +53,7 @@ svc_layer_diff_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t 
 }
 
 // A[b] = (sum_l keep_l A_l) / (sum_l keep_l + 1e-5) * seg[b],  keep_l = d[b,l] <= mean_l d[b,:]
-__global__ void svc_seg_mean_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int N, int l0, int nl,
+__global__ void svc_seg_mean_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int N, int l0, int nl,
                                     const float* __restrict__ seg, const float* __restrict__ d, float* __restrict__ A) {
     const int np = N - 1;
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, b = blockIdx.z;
@@ -61,7 +61,7 @@ __global__ void svc_seg_mean_kernel(const float* __restrict__ attn, int64_t stri
     float mean = 0.f;
     for (int l = 0; l < nl; ++l) mean += d[b * nl + l];
     mean /= (float)nl;
-    const float* p = attn + (int64_t)l0 * stride_l + (int64_t)b * stride_b + (int64_t)(i + 1) * N + (j + 1);
+    const float* p = attn + (int64_t)l0 * stride_l + (int64_t)b * stride_b + (int64_t)(i + 1) * stride_r + (j + 1);
     float s = 0.f, cnt = 0.f;
     for (int l = 0; l < nl; ++l)
         if (d[b * nl + l] <= mean) { s += __ldcs(p + (int64_t)l * stride_l); cnt += 1.f; }
@@ -293,28 +293,28 @@ extern "C" int excel_svc_build_trans(const float* A, const float* r, const float
     return check_launch("svc_build_trans_kernel");
 }
 
-extern "C" int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N,
+extern "C" int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int L, int B, int N,
                                         int attn_layers, float* A, void* stream) {
-    XL_REQUIRE(L >= 1 && B >= 0 && N >= 2 && attn_layers >= 1, "svc_mean_attention: bad shape L=%d B=%d N=%d", L, B, N);
+    XL_REQUIRE(L >= 1 && B >= 0 && N >= 2 && attn_layers >= 1 && stride_r >= N, "svc_mean_attention: bad shape L=%d B=%d N=%d", L, B, N);
     if (B == 0) return 0;
     const int nl = attn_layers < L ? attn_layers : L, np = N - 1;
     XL_REQUIRE(np <= 65535 && B <= 65535, "svc_mean_attention: grid too large");
     dim3 grid(ceil_div(np, 256), np, B);
-    svc_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(attn, stride_l, stride_b, N, L - nl, nl, A);
+    svc_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(attn, stride_l, stride_b, stride_r, N, L - nl, nl, A);
     return check_launch("svc_mean_kernel");
 }
 
-extern "C" int excel_svc_seg_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N,
+extern "C" int excel_svc_seg_attention(const float* attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int L, int B, int N,
                                        int attn_layers, const float* seg_attn, float* diff_ws, float* A, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    XL_REQUIRE(L >= 1 && B >= 0 && N >= 2 && attn_layers >= 1 && seg_attn && diff_ws, "svc_seg_attention: bad arguments");
+    XL_REQUIRE(L >= 1 && B >= 0 && N >= 2 && attn_layers >= 1 && seg_attn && diff_ws && stride_r >= N, "svc_seg_attention: bad arguments");
     if (B == 0) return 0;
     const int nl = attn_layers < L ? attn_layers : L, np = N - 1;
     XL_REQUIRE(np <= 65535 && B <= 65535, "svc_seg_attention: grid too large");
-    svc_layer_diff_kernel<<<dim3(nl, B), 1024, 0, st>>>(attn, stride_l, stride_b, N, L - nl, seg_attn, diff_ws);
+    svc_layer_diff_kernel<<<dim3(nl, B), 1024, 0, st>>>(attn, stride_l, stride_b, stride_r, N, L - nl, seg_attn, diff_ws);
     if (int e = check_launch("svc_layer_diff_kernel")) return e;
     dim3 grid(ceil_div(np, 256), np, B);
-    svc_seg_mean_kernel<<<grid, 256, 0, st>>>(attn, stride_l, stride_b, N, L - nl, nl, seg_attn, diff_ws, A);
+    svc_seg_mean_kernel<<<grid, 256, 0, st>>>(attn, stride_l, stride_b, stride_r, N, L - nl, nl, seg_attn, diff_ws, A);
     return check_launch("svc_seg_mean_kernel");
 }
 

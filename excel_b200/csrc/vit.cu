@@ -22,8 +22,9 @@ namespace xl {
 // subnormal range (absolute resolution 6e-8); the exact factor 2^-10 is folded into the GEMM's alpha.
 constexpr float kProbScale = 1024.f;
 
+// hi saturates at fp16's largest finite value, so |v| up to 2 x 65504 still splits into finite halves (no inf - inf = NaN)
 __device__ __forceinline__ void split_store(__half* hi, __half* lo, float v) {
-    const __half h = __float2half_rn(v);
+    const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     *hi = h;
     *lo = __float2half_rn(v - __half2float(h));
 }
@@ -127,21 +128,29 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 }
 
 struct Ws {  // workspace carve-up
-    float *pos, *m, *pnew, *pad, *mid, *x0;
+    float *pos, *m, *pnew, *part, *mid, *x0;
     __half *col, *h, *qkv, *pn, *o, *o2, *u;
 };
 
 static size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// partial head-sum maps of a split attention launch (small batches): [ngrp][B,N,Npad]
+static size_t part_bytes(int B, int N, int H) {
+    int hpi, gsplit;
+    attn_pv_plan(B, H, N, &hpi, &gsplit);
+    return gsplit ? (size_t)((H + hpi - 1) / hpi) * B * N * ((N + 3) & ~3) * 4 : 0;
+}
 
 static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     const size_t BN = (size_t)B * N, np = (size_t)((N + 63) & ~63);
     size_t t = 0;
     t += align256((size_t)N * D * 4);                 // pos
     t += align256((size_t)3 * B * H * N * 4);         // softmax row statistic (up to 3 score sets)
-    t += 2 * align256((size_t)B * N * ((N + 3) & ~3) * 4); // pnew, pad (row-padded attention maps, TMA targets)
+    t += align256((size_t)B * N * ((N + 3) & ~3) * 4); // pnew (row-padded new-path map: LVC branch only)
+    t += align256(part_bytes(B, N, H));               // part
     t += 2 * align256(BN * D * 4);                    // mid, x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
-    t += 3 * align256(BN * 2 * D * 2);                // h, o, o2
+    t += align256(BN * 2 * D * 2) + align256(2 * BN * 2 * D * 2);   // h; o2 | o
     t += align256(BN * 6 * D * 2);                    // qkv
     t += align256(BN * 2 * np * 2);                   // pn
     t += align256(BN * 8 * D * 2);                    // u
@@ -149,7 +158,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
 }
 
 struct Maps {  // tensor maps of the activation operands (built once per forward)
-    CUtensorMap col, h, qkv_a, qkv_v, pn, o, o2, u;
+    CUtensorMap col, h, qkv_a, qkv_v, pn, o, o2, oo, u;   // oo: o2 | o as one [2 BN, 2 D] matrix (merged out_proj)
 };
 
 struct Ctx {
@@ -165,53 +174,71 @@ static int layernorm(const Ctx& c, const float* x, const float* w, const float* 
     return check_launch("layernorm_kernel");
 }
 
-// y = act(x W^T + bias) (+ residual): x split [M, 2K] (map ma), W split [Nout, 2K] (map mw)
-static int linear(const Ctx& c, const CUtensorMap& ma, const CUtensorMap& mw, int K, int Nout, const float* bias, int act,
-                  const float* residual, float* y, __half* ys) {
+// Tile width of a [M, Nout] GEMM: the widest tile (least L2 -> SM operand traffic per MMA) that still gives every SM a tile;
+// small batches (the per-image loops of the drop-in surface: M = N tokens) fall back to narrower tiles.
+static int pick_bn(int64_t M, int Nout, int batch = 1) {
+    const int64_t mt = ceil_div64(M, 128) * batch;
+    if (Nout % 256 == 0 && mt * (Nout / 256) >= kNumSMs) return 256;
+    if (mt * ceil_div(Nout, 128) >= (kNumSMs * 2) / 3 || Nout <= 64) return Nout <= 64 ? 64 : 128;
+    return 64;
+}
+
+// A weight matrix in the engine's operand format: split fp16 [out, 2 K] (hi | lo) of  wscale * W  (wscale: the power of two
+// chosen at load time that puts max|W| at 2^13..2^14, clear of fp16's subnormal range; folded back through alpha).
+struct Wt { const void* ws; float scale; };
+
+// y = act(x W^T + bias) (+ residual): x split [M rows per batch, 2K] (map ma), W split [Nout, 2K].
+// batch = 2 runs two activations (row blocks a_row1 apart in ma) against the SAME weights into outputs c1 floats apart.
+static int linear(const Ctx& c, const CUtensorMap& ma, Wt w, int K, int Nout, const float* bias, int act,
+                  const float* residual, float* y, __half* ys, int batch = 1, int64_t c1 = 0) {
     TcParams p = {};
     p.M = (int)c.BN; p.N = Nout; p.kblocks = K / 64; p.a_lo_off = K; p.b_lo_off = K; p.nb2 = 1;
-    p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f; p.act = act;
+    p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f / w.scale; p.act = act;
     p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
-    const int bn = Nout % 256 == 0 ? 256 : 128;
-    return tc_gemm(ma, mw, p, 1, bn, c.st);
+    if (batch > 1) { p.a_row1 = (int)c.BN; p.c1 = c1; }
+    const int bn = pick_bn(c.BN, Nout, batch);
+    CUtensorMap mw;
+    if (int e = make_operand_map(&mw, w.ws, Nout, 2 * K, 2 * K, bn == 64 ? 64 : 128)) return e;
+    return tc_gemm(ma, mw, p, batch, bn, c.st);
 }
 
 // Row statistics of softmax(scale * X_t,h Y_t,h^T) for `ntypes` score sets (column blocks xo[t], yo[t] of qkv_s) and, unless
 // stats_only, the row-padded map  out[b] = coef * sum_t sum_h softmax(...)  -- the scores are never materialised (attn_tc.cu).
-static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float scale, float* out_padded, float coef,
-                  bool stats_only) {
+static int scores(const Ctx& c, int ntypes, const int* xo, const int* yo, float scale, float* out_padded, __half* out_split,
+                  float coef, bool stats_only) {
     AttnParams p = {};
     p.B = c.B; p.H = c.H; p.N = c.N; p.ntypes = ntypes; p.lo_off = 3 * c.D;
     for (int t = 0; t < ntypes; ++t) { p.xo[t] = xo[t]; p.yo[t] = yo[t]; }
     p.alpha = scale * 1.4426950408889634f;  // exp2 domain
-    p.m = c.w.m; p.out = out_padded; p.coef = coef;
+    p.m = c.w.m; p.out = out_padded; p.coef = coef; p.out_split = out_split; p.np = c.np;
     return attn_scores(c.m.qkv_a, p, c.st, stats_only);
 }
 
-// Original-path attention: stats pass, then ONE fused kernel (attn_pv.cu): out = coef * sum_h softmax(q_h k_h^T) and
-// o_s[b, :, h*dh..] = softmax(q_h k_h^T) V[b,h] -- the per-head probabilities stay in tensor memory.
+// Original-path attention: stats pass, then ONE fused kernel (attn_pv.cu): out = coef * sum_h softmax(q_h k_h^T), written
+// straight into the API's attention tensor [B,N,Npad], and o_s[b, :, h*dh..] = softmax(q_h k_h^T) V[b,h] -- the per-head
+// probabilities stay in tensor memory.
 static int attention_qk(const Ctx& c, float scale, float* out, float coef) {
     const int qx[1] = {0}, ky[1] = {c.D};
-    if (int e = scores(c, 1, qx, ky, scale, nullptr, 0.f, true)) return e;
+    if (int e = scores(c, 1, qx, ky, scale, nullptr, nullptr, 0.f, true)) return e;
     AttnPvParams q = {};
     q.B = c.B; q.H = c.H; q.N = c.N; q.D = c.D; q.xo = 0; q.yo = c.D; q.vo = 2 * c.D; q.lo_off = 3 * c.D;
-    q.alpha = scale * 1.4426950408889634f; q.ml = c.w.m; q.out = c.w.pad; q.coef = coef; q.o = c.w.o;
-    if (int e = attn_pv(c.m.qkv_a, q, c.st)) return e;
-    return attn_compact(c.w.pad, (c.N + 3) & ~3, out, c.N, c.BN, c.st);   // API layout [B,N,N]
+    q.alpha = scale * 1.4426950408889634f; q.ml = c.w.m; q.out = out; q.coef = coef; q.o = c.w.o;
+    attn_pv_plan(c.B, c.H, c.N, &q.hpi, &q.gsplit);
+    q.part = c.w.part;
+    return attn_pv(c.m.qkv_a, q, c.st);
 }
 
 // ln_1 -> in_proj -> split qkv (V is consumed in place, MN-major, by the attention kernel and the new-path GEMM)
-static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw, const CUtensorMap& m_in) {
+static int qkv_stage(const Ctx& c, const float* src, const ExcelVitLayer& Lw) {
     if (int e = layernorm(c, src, Lw.ln1_w, Lw.ln1_b, c.w.h)) return e;
-    return linear(c, c.m.h, m_in, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv);
+    return linear(c, c.m.h, Wt{Lw.in_ws, Lw.in_scale}, c.D, 3 * c.D, Lw.in_b, 0, nullptr, nullptr, c.w.qkv);
 }
 
 // feat = mid + c_proj(QuickGELU(c_fc(ln_2(mid))))
-static int mlp_stage(const Ctx& c, const float* mid, const ExcelVitLayer& Lw, const CUtensorMap& m_fc, const CUtensorMap& m_proj,
-                     float* feat) {
+static int mlp_stage(const Ctx& c, const float* mid, const ExcelVitLayer& Lw, float* feat) {
     if (int e = layernorm(c, mid, Lw.ln2_w, Lw.ln2_b, c.w.h)) return e;
-    if (int e = linear(c, c.m.h, m_fc, c.D, 4 * c.D, Lw.fc_b, 1, nullptr, nullptr, c.w.u)) return e;
-    return linear(c, c.m.u, m_proj, 4 * c.D, c.D, Lw.proj_b, 0, mid, feat, nullptr);
+    if (int e = linear(c, c.m.h, Wt{Lw.fc_ws, Lw.fc_scale}, c.D, 4 * c.D, Lw.fc_b, 1, nullptr, nullptr, c.w.u)) return e;
+    return linear(c, c.m.u, Wt{Lw.proj_ws, Lw.proj_scale}, 4 * c.D, c.D, Lw.proj_b, 0, mid, feat, nullptr);
 }
 
 }  // namespace xl
@@ -223,13 +250,15 @@ extern "C" int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int
     return (int64_t)ws_bytes(B, N, D, heads, (3 * patch * patch + 63) & ~63);
 }
 
-extern "C" int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, void* out, void* stream) {
-    return split_f16(x, ldx, rows, cols, Kp, reinterpret_cast<__half*>(out), (cudaStream_t)stream);
+extern "C" int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, float scale, void* out, void* stream) {
+    XL_REQUIRE(scale > 0.f, "split_f16: scale must be positive");
+    return split_f16(x, ldx, rows, cols, Kp, reinterpret_cast<__half*>(out), (cudaStream_t)stream, scale);
 }
 
 extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, int64_t img_stride_b, int64_t img_stride_c,
                                  int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes,
-                                 float* tokens, float* attn, float* feats, const float* lvc_attn, void* stream) {
+                                 float* tokens, float* attn, int64_t attn_row_pitch, float* feats, const float* lvc_attn,
+                                 void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     XL_REQUIRE(Wt != nullptr, "vit_forward: null weights");
     const int L = Wt->layers, D = Wt->width, H = Wt->heads, P = Wt->patch, E = Wt->embed, g0 = Wt->grid0,
@@ -238,11 +267,14 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                "vit_forward: unsupported geometry L=%d D=%d H=%d P=%d (head dim must be 64)", L, D, H, P);
     XL_REQUIRE(nsur >= 1 && nsur < L, "vit_forward: n_surgery=%d must be in [1, L-1]", nsur);
     XL_REQUIRE(B >= 0 && S >= P && S % P == 0, "vit_forward: image size %d is not a multiple of the patch size %d", S, P);
-    XL_REQUIRE(Wt->conv1_s && Wt->proj_t_s, "vit_forward: split weights missing (excel_split_f16 at load time)");
+    XL_REQUIRE(Wt->conv1_s && Wt->proj_t_s && Wt->conv1_scale > 0.f && Wt->proj_t_scale > 0.f,
+               "vit_forward: split weights / scales missing (excel_split_f16 at load time)");
     if (B == 0) return 0;
     const int g = S / P, npatch = g * g, N = npatch + 1, KK = 3 * P * P, KKp = (KK + 63) & ~63, dh = D / H, first = L - nsur;
-    const int np = (N + 63) & ~63;
+    const int np = (N + 63) & ~63, Npad = (N + 3) & ~3;
     const int64_t BN = (int64_t)B * N, ND = (int64_t)N * D;
+    XL_REQUIRE(attn_row_pitch == Npad && (reinterpret_cast<uintptr_t>(attn) & 15) == 0,
+               "vit_forward: attn must be [L,B,N,%d] (row pitch round_up(N,4): TMA store target), 16 B-aligned", Npad);
     XL_REQUIRE(workspace_bytes >= (int64_t)ws_bytes(B, N, D, H, KKp), "vit_forward: workspace too small");
     XL_REQUIRE(npatch <= 65535 && B <= 65535 && (int64_t)B * H * N < (1ll << 31) && BN * 6 * D < (1ll << 31),
                "vit_forward: problem too large");
@@ -256,14 +288,14 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         auto take = [&](size_t bytes) { uint8_t* r = p; p += align256(bytes); return r; };
         c.w.pos = (float*)take((size_t)N * D * 4);
         c.w.m = (float*)take((size_t)3 * B * H * N * 4);
-        c.w.pnew = (float*)take((size_t)B * N * ((N + 3) & ~3) * 4);
-        c.w.pad = (float*)take((size_t)B * N * ((N + 3) & ~3) * 4);
+        c.w.pnew = (float*)take((size_t)B * N * Npad * 4);
+        c.w.part = (float*)take(part_bytes(B, N, H));
         c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
         c.w.col = (__half*)take((size_t)B * npatch * 2 * KKp * 2);
         c.w.h = (__half*)take(BN * 2 * D * 2);
-        c.w.o = (__half*)take(BN * 2 * D * 2);
-        c.w.o2 = (__half*)take(BN * 2 * D * 2);
+        c.w.o2 = (__half*)take(2 * BN * 2 * D * 2);   // o2 | o contiguous: the merged out_proj reads them as one [2 BN, 2 D] matrix
+        c.w.o = c.w.o2 + BN * 2 * D;
         c.w.qkv = (__half*)take(BN * 6 * D * 2);
         c.w.pn = (__half*)take(BN * 2 * np * 2);
         c.w.u = (__half*)take(BN * 8 * D * 2);
@@ -277,6 +309,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         e |= make_operand_map(&c.m.pn, c.w.pn, BN, 2 * np, 2 * np, 128);
         e |= make_operand_map(&c.m.o, c.w.o, BN, 2 * D, 2 * D, 128);
         e |= make_operand_map(&c.m.o2, c.w.o2, BN, 2 * D, 2 * D, 128);
+        e |= make_operand_map(&c.m.oo, c.w.o2, 2 * BN, 2 * D, 2 * D, 128);
         e |= make_operand_map(&c.m.u, c.w.u, BN, 8 * D, 8 * D, 128);
         if (e) return e;
     }
@@ -290,7 +323,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         if (int e = make_operand_map(&m_conv, Wt->conv1_s, D, 2 * KKp, 2 * KKp, 128)) return e;
         TcParams p = {};  // patches of image b land in rows 1..npatch of x0[b]
         p.M = npatch; p.N = D; p.kblocks = KKp / 64; p.a_lo_off = KKp; p.b_lo_off = KKp; p.nb2 = 1; p.a_row1 = npatch;
-        p.C = c.w.x0 + D; p.ldc = D; p.c1 = ND; p.alpha = 1.f;
+        p.C = c.w.x0 + D; p.ldc = D; p.c1 = ND; p.alpha = 1.f / Wt->conv1_scale;
         if (int e = tc_gemm(c.m.col, m_conv, p, B, 128, st)) return e;
         const float* pos = Wt->pos;
         if (g != g0) {
@@ -308,52 +341,53 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
     const float* x = c.w.x0;  // current single-path state (blocks before the surgery)
     for (int l = 0; l < L; ++l) {
         const ExcelVitLayer& Lw = Wt->blocks[l];
-        XL_REQUIRE(Lw.in_ws && Lw.out_ws && Lw.fc_ws && Lw.proj_ws, "vit_forward: split weights of block %d missing", l);
-        CUtensorMap m_in, m_out, m_fc, m_proj;
-        {
-            int e = 0;
-            e |= make_operand_map(&m_in, Lw.in_ws, 3 * D, 2 * D, 2 * D, 128);
-            e |= make_operand_map(&m_out, Lw.out_ws, D, 2 * D, 2 * D, 128);
-            e |= make_operand_map(&m_fc, Lw.fc_ws, 4 * D, 2 * D, 2 * D, 128);
-            e |= make_operand_map(&m_proj, Lw.proj_ws, D, 8 * D, 8 * D, 128);
-            if (e) return e;
-        }
-        float* attn_l = attn + (int64_t)l * B * N * N;
+        XL_REQUIRE(Lw.in_ws && Lw.out_ws && Lw.fc_ws && Lw.proj_ws && Lw.in_scale > 0.f && Lw.out_scale > 0.f && Lw.fc_scale > 0.f &&
+                   Lw.proj_scale > 0.f, "vit_forward: split weights / scales of block %d missing", l);
+        const struct Wt w_out = {Lw.out_ws, Lw.out_scale};
+        float* attn_l = attn + (int64_t)l * B * N * Npad;
         float* feat_l = feats + (int64_t)l * BN * D;
         if (l < first) {  // ---- standard block (:332-337)
-            if (int e = qkv_stage(c, x, Lw, m_in)) return e;
+            if (int e = qkv_stage(c, x, Lw)) return e;
             if (int e = attention_qk(c, scale, attn_l, 1.f / H)) return e;    // need_weights: head mean; o = attn @ v
-            if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
-            if (int e = mlp_stage(c, c.w.mid, Lw, m_fc, m_proj, feat_l)) return e;
+            if (int e = linear(c, c.m.o, w_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
+            if (int e = mlp_stage(c, c.w.mid, Lw, feat_l)) return e;
             x = feat_l;
         } else {  // ---- surgery block (:309-330, Attention.forward :95-159)
             float* xnew = feats + (int64_t)(first - 1) * BN * D;              // new path, accumulates x_res in place
             float* src = feats + (int64_t)(l - 1) * BN * D;                   // X_{first-1} or previous x_ori
-            if (int e = qkv_stage(c, src, Lw, m_in)) return e;
-            // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146)
-            if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, 1.f / 3.f, false)) return e;
-            if (lvc_attn) {   // LVC: + ex_attn on every head's patch block, then summed over heads (:139-146) == + H * ex_attn
+            if (int e = qkv_stage(c, src, Lw)) return e;
+            // new path: (softmax(qq^T) + softmax(kk^T) + softmax(vv^T))/3 summed over heads (:119-125,146).  The map pass
+            // writes the 2^10-scaled map straight into the split-fp16 A operand of the P V GEMM below; only the LVC branch
+            // (which adds ex_attn to the fp32 map first) takes the fp32 map + split pass.
+            if (!lvc_attn) {
+                if (int e = scores(c, 3, self_xy, self_xy, scale, nullptr, c.w.pn, 1.f / 3.f, false)) return e;
+            } else {   // LVC: + ex_attn on every head's patch block, then summed over heads (:139-146) == + H * ex_attn
+                if (int e = scores(c, 3, self_xy, self_xy, scale, c.w.pnew, nullptr, 1.f / 3.f, false)) return e;
                 dim3 grid(ceil_div(N - 1, 256), N - 1, B);
-                lvc_add_kernel<<<grid, 256, 0, st>>>(lvc_attn, N - 1, (float)H, c.w.pnew, (N + 3) & ~3, N);
+                lvc_add_kernel<<<grid, 256, 0, st>>>(lvc_attn, N - 1, (float)H, c.w.pnew, Npad, N);
                 if (int e = check_launch("lvc_add_kernel")) return e;
+                if (int e = split_f16(c.w.pnew, Npad, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             }
-            if (int e = split_f16(c.w.pnew, (N + 3) & ~3, (int)BN, N, np, c.w.pn, st, kProbScale)) return e;
             {   // x = attn @ v with the head-summed map applied to every head's v (:149): [N,N] x [N,D] per image
                 TcParams p = {};
                 // B operand = V [keys, D] in place inside the split qkv matrix (MN-major): no transpose pass
                 p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.nb2 = 1;
                 p.a_row1 = N; p.b_mn = 1; p.b_row1 = N; p.b_col0 = 2 * D; p.b_lo_off = 3 * D; p.alpha = 1.f / kProbScale;
                 p.Cs = c.w.o2; p.lds = 2 * D; p.cs1 = (int64_t)N * 2 * D; p.cs_lo_off = D;
-                if (int e = tc_gemm(c.m.pn, c.m.qkv_v, p, B, D % 256 == 0 ? 256 : 128, st)) return e;
+                if (int e = tc_gemm(c.m.pn, c.m.qkv_v, p, B, pick_bn(N, D, B), st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
             if (int e = attention_qk(c, scale, attn_l, 1.f)) return e;          // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
             float* mid = (l == first) ? c.w.mid : src;
-            if (int e = linear(c, c.m.o, m_out, D, D, Lw.out_b, 0, src, mid, nullptr)) return e;
-            if (int e = linear(c, c.m.o2, m_out, D, D, Lw.out_b, 0, xnew, xnew, nullptr)) return e;       // x += x_res (:319,329)
-            if (int e = mlp_stage(c, mid, Lw, m_fc, m_proj, feat_l)) return e;                           // x_ori
+            if (l == first) {   // src IS xnew here: the two products read / update the same rows, so they stay two launches
+                if (int e = linear(c, c.m.o, w_out, D, D, Lw.out_b, 0, src, mid, nullptr)) return e;
+                if (int e = linear(c, c.m.o2, w_out, D, D, Lw.out_b, 0, xnew, xnew, nullptr)) return e;   // x += x_res (:319,329)
+            } else {            // one launch: [o2 | o] x out_proj^T -> xnew += .., src += ..  (in place, disjoint buffers)
+                if (int e = linear(c, c.m.oo, w_out, D, D, Lw.out_b, 0, xnew, xnew, nullptr, 2, src - xnew)) return e;
+            }
+            if (int e = mlp_stage(c, mid, Lw, feat_l)) return e;                                         // x_ori
         }
     }
     // x[0] = x_ori[0] (:442), ln_post, @ proj (:445-446)
@@ -368,6 +402,6 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
     if (int e = make_operand_map(&m_pt, Wt->proj_t_s, E, 2 * D, 2 * D, E <= 64 ? 64 : 128)) return e;
     TcParams p = {};
     p.M = (int)BN; p.N = E; p.kblocks = D / 64; p.a_lo_off = D; p.b_lo_off = D; p.nb2 = 1;
-    p.C = tokens; p.ldc = E; p.alpha = 1.f;
+    p.C = tokens; p.ldc = E; p.alpha = 1.f / Wt->proj_t_scale;
     return tc_gemm(c.m.h, m_pt, p, 1, E <= 64 ? 64 : 128, st);
 }

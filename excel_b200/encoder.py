@@ -6,6 +6,7 @@
 module, so the reference's ``ExCEL_model.encoder`` can be used as is.
 """
 import ctypes
+import math
 
 import torch
 
@@ -63,9 +64,10 @@ class SurgeryViT:
         for i in range(L):
             for f, name in _BLOCK_FIELDS:
                 setattr(self._blocks[i], f, self.W["blocks.%d.%s" % (i, name)].data_ptr())
-            for f, name in (("in_ws", "in_proj_weight"), ("out_ws", "out_proj.weight"), ("fc_ws", "c_fc.weight"),
-                            ("proj_ws", "c_proj.weight")):
-                setattr(self._blocks[i], f, self._split("blocks.%d.%s" % (i, name)).data_ptr())
+            for f, name in (("in", "in_proj_weight"), ("out", "out_proj.weight"), ("fc", "c_fc.weight"), ("proj", "c_proj.weight")):
+                ws, scale = self._split("blocks.%d.%s" % (i, name))
+                setattr(self._blocks[i], f + "_ws", ws.data_ptr())
+                setattr(self._blocks[i], f + "_scale", scale)
         w = _lib.VitWeights()
         w.layers, w.width, w.heads, w.patch, w.embed, w.grid0, w.n_surgery = L, self.width, H, P, self.embed, self.grid0, n_surgery
         for f, name in (("conv1", "conv1.weight"), ("cls", "class_embedding"), ("pos", "positional_embedding"),
@@ -74,22 +76,28 @@ class SurgeryViT:
             setattr(w, f, self.W[name].data_ptr())
         self.W["conv1.flat"] = self.W["conv1.weight"].reshape(self.width, -1).contiguous()
         self.W["proj.t"] = self.W["proj"].t().contiguous()
-        w.conv1_s = self._split("conv1.flat").data_ptr()
-        w.proj_t_s = self._split("proj.t").data_ptr()
+        (c1, w.conv1_scale), (pt, w.proj_t_scale) = self._split("conv1.flat"), self._split("proj.t")
+        w.conv1_s, w.proj_t_s = c1.data_ptr(), pt.data_ptr()
         w.blocks = ctypes.cast(self._blocks, ctypes.POINTER(_lib.VitLayer))
         self._w = w
         self._ws = None
 
     def _split(self, name):
-        """fp32 weight [out, in] -> split fp16 [out, 2*round_up(in, 64)] (hi | lo) on the device."""
+        """fp32 weight [out, in] -> (split fp16 [out, 2*round_up(in, 64)] (hi | lo) of scale * W on the device, scale).
+        scale = the power of two that puts max|W| at 2^13..2^14: trained weights of magnitude ~0.02 would otherwise have
+        their lo halves in fp16's subnormal range (absolute resolution 6e-8 instead of 22 significant bits)."""
         x = self.W[name]
         rows, cols = x.shape
         kp = (cols + 63) // 64 * 64
+        amax = float(x.abs().max())
+        if not math.isfinite(amax):
+            raise RuntimeError(f"SurgeryViT: weight {name} contains inf / nan")
+        scale = 2.0 ** (13 - math.frexp(amax)[1] + 1) if amax > 0 else 1.0      # amax * scale in [2^13, 2^14)
         out = torch.empty((rows, 2 * kp), dtype=torch.float16, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.call("excel_split_f16", _lib.ptr(x), x.stride(0), rows, cols, kp, _lib.ptr(out), _lib.stream())
+            _lib.call("excel_split_f16", _lib.ptr(x), x.stride(0), rows, cols, kp, scale, _lib.ptr(out), _lib.stream())
         self.Ws[name] = out
-        return out
+        return out, scale
 
     @classmethod
     def from_visual(cls, visual, n_surgery=5, device="cuda"):
@@ -151,12 +159,15 @@ class SurgeryViT:
                 self._ws = self._alloc_ws(B, S)
             ws = self._ws
         tokens = torch.empty((B, N, self.embed), dtype=torch.float32, device=self.device)
-        attn = torch.empty((self.layers, B, N, N), dtype=torch.float32, device=self.device)
+        # the attention maps are written by TMA stores: rows padded to a multiple of 16 B; callers get the [.., :N] view
+        # (the reference's consumers slice / index this tensor anyway: attn_weights[:, i], [-6:, 1:, 1:], ...)
+        npad = (N + 3) // 4 * 4
+        attn = torch.empty((self.layers, B, N, npad), dtype=torch.float32, device=self.device)
         feats = torch.empty((self.layers, B, N, self.width), dtype=torch.float32, device=self.device)
         _lib.call("excel_vit_forward", ctypes.byref(self._w), _lib.ptr(img), img.stride(0), img.stride(1), img.stride(2), B, S,
-                  _lib.ptr(ws), ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), _lib.ptr(feats), _lib.ptr(lvc_attn),
+                  _lib.ptr(ws), ws.numel() * 4, _lib.ptr(tokens), _lib.ptr(attn), npad, _lib.ptr(feats), _lib.ptr(lvc_attn),
                   _lib.stream())
-        return tokens, attn, feats
+        return tokens, attn[..., :N], feats
 
     __call__ = forward
 

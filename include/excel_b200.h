@@ -58,15 +58,15 @@ int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_
 /* ---------------------------------------------------------------- SVC (utils/affutils.py) ------ */
 
 /* utils/affutils.py:180,197 (training-free branch of refine_cams_with_aff): A[b] = mean over the last
- * `attn_layers` of attn[l, b, 1:, 1:].  attn [L,B,N,N] with element strides (stride_l, stride_b, N, 1);
- * A [B, N-1, N-1]. */
-int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N,
+ * `attn_layers` of attn[l, b, 1:, 1:].  attn [L,B,N,N] with element strides (stride_l, stride_b, stride_r, 1) -- the
+ * encoder returns a row pitch of round_up(N,4) (excel_vit_forward); A [B, N-1, N-1]. */
+int excel_svc_mean_attention(const float* attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int L, int B, int N,
                              int attn_layers, float* A, void* stream);
 
 /* utils/affutils.py:182-195 (the seg_attn / LVC branch of refine_cams_with_aff): per image keep the layers l of the
  * last `attn_layers` whose sum(seg_attn - attn_l[1:,1:]) is <= the mean over those layers;
  * A = (sum of kept layers) / (number kept + 1e-5) * seg_attn.  seg_attn [B,N-1,N-1]; diff_ws [B*attn_layers]. */
-int excel_svc_seg_attention(const float* attn, int64_t stride_l, int64_t stride_b, int L, int B, int N, int attn_layers,
+int excel_svc_seg_attention(const float* attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int L, int B, int N, int attn_layers,
                             const float* seg_attn, float* diff_ws, float* A, void* stream);
 
 /* utils/affutils.py:11-16 (compute_trans_mat, the 1 + 2 rounds of column / row normalisation) in scaling
@@ -105,9 +105,13 @@ int excel_svc_cams_to_planes(const float* refined, int Q, int gh, int gw, const 
 int excel_token_normalize(const float* tok, int B, int N, int E, float* norm_ws, float* out, void* stream);
 
 /* clip/clip.py:288-310 (clip_feature_surgery, redundant_feats=None): feats [B,N,E], text [T,E] ->
- * out [B,N,T], min-max normalised over all N tokens per (b,t), no epsilon.  S_ws [B,N,T]. */
-int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, float* S_ws, float* out,
-                      void* stream);
+ * out [B,N,T], min-max normalised over all N tokens per (b,t), no epsilon.  The similarity GEMM S = feats text^T runs on the
+ * tcgen05 engine (split-fp16 operands, pre-scaled on the device by a power of two of their max-abs); the w / redundant-term
+ * row epilogue and the column min-max are two coalesced passes.  workspace: excel_cam_workspace_bytes(B,N,E,T) bytes,
+ * 256 B-aligned.  T <= 512. */
+int64_t excel_cam_workspace_bytes(int B, int N, int E, int T);
+int excel_cam_surgery(const float* feats, const float* text, int B, int N, int E, int T, void* workspace,
+                      int64_t workspace_bytes, float* out, void* stream);
 
 /* utils/camutils.py:19-26 (cure_attr_map_flip): attr_2b [2B, gh*gw, K] = maps of [x, flip(x)] -> out [B, gh*gw, K]:
  * element-max of the un-flipped pair, minus its per-(b,k) spatial min, divided by (max + 1e-5). */
@@ -120,8 +124,11 @@ int excel_flip_merge(const float* attr_2b, int B, int gh, int gw, int K, float* 
  * :396-405); out_w/out_b = attn.out_proj (or Attention.proj). */
 typedef struct {
     const float *ln1_w, *ln1_b, *in_w, *in_b, *out_w, *out_b, *ln2_w, *ln2_b, *fc_w, *fc_b, *proj_w, *proj_b;
-    /* split-fp16 copies of the four weight matrices (excel_split_f16 at load time): [out, 2*in] halves, hi | lo */
+    /* split-fp16 copies of the four weight matrices (excel_split_f16 at load time): [out, 2*in] halves, hi | lo, of
+     * x_scale * W; x_scale is a power of two that puts max|W| at 2^13..2^14 (fp16's normal range for both halves) and is
+     * divided out again by the GEMM's alpha */
     const void *in_ws, *out_ws, *fc_ws, *proj_ws;
+    float in_scale, out_scale, fc_scale, proj_scale;
 } ExcelVitLayer;
 
 /* VisionTransformer (clip/clip_surgery_model.py:374-448).  conv1 [width, 3*patch*patch]; cls [width];
@@ -130,25 +137,29 @@ typedef struct {
 typedef struct {
     int layers, width, heads, patch, embed, grid0, n_surgery;
     const float *conv1, *cls, *pos, *ln_pre_w, *ln_pre_b, *ln_post_w, *ln_post_b, *proj;
-    const void *conv1_s, *proj_t_s;   /* split-fp16 conv1 [width, 2*Kp] and proj^T [embed, 2*width] */
+    const void *conv1_s, *proj_t_s;   /* split-fp16 conv1 [width, 2*Kp] and proj^T [embed, 2*width], pre-scaled like the blocks' */
+    float conv1_scale, proj_t_scale;
     const ExcelVitLayer* blocks;
 } ExcelVitWeights;
 
 int64_t excel_vit_workspace_bytes(int B, int S, int patch, int D, int heads);
 
-/* fp32 [rows, cols] (row pitch ldx) -> split fp16 [rows, 2*Kp] (hi | lo, zero padded), Kp % 64 == 0: the
- * operand format of the tcgen05 GEMM engine (x = hi + lo keeps 22 significant bits). */
-int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, void* out, void* stream);
+/* fp32 [rows, cols] (row pitch ldx) -> split fp16 [rows, 2*Kp] (hi | lo, zero padded) of scale * x, Kp % 64 == 0: the
+ * operand format of the tcgen05 GEMM engine (x = hi + lo keeps 22 significant bits while both halves are normal fp16
+ * numbers: 6.1e-5 <= |lo|, |hi| <= 65504 -- pick `scale` accordingly; hi saturates instead of overflowing to inf). */
+int excel_split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, float scale, void* out, void* stream);
 
 /* VisionTransformer.forward + Transformer.forward (clip/clip_surgery_model.py:418-448, 346-371) as called by
  * clip.generate_clip_fts (clip/clip.py:348-358), for img [B,3,S,S] (element strides b, c, y; x contiguous).
  * Outputs: tokens [B,N,embed] (BEFORE the token-axis normalisation of clip.py:353 -> excel_token_normalize),
- * attn [layers,B,N,N], feats [layers,B,N,width] with the reference's view aliasing.
+ * attn [layers,B,N,attn_row_pitch] with attn_row_pitch = round_up(N,4) floats (the attention kernels write the maps with TMA
+ * stores, whose row pitch must be a multiple of 16 B; columns >= N are padding -- callers view [.., :N]),
+ * feats [layers,B,N,width] with the reference's view aliasing.
  * lvc_attn: NULL, or the LVC bias ex_attn [B,N-1,N-1] of excel_lvc_attention (Attention.forward with ex_feats,
  * clip/clip_surgery_model.py:127-141): added to every head's patch block of the surgery blocks' new-path attention. */
 int excel_vit_forward(const ExcelVitWeights* w, const float* img, int64_t img_stride_b, int64_t img_stride_c,
                       int64_t img_stride_y, int B, int S, float* workspace, int64_t workspace_bytes, float* tokens,
-                      float* attn, float* feats, const float* lvc_attn, void* stream);
+                      float* attn, int64_t attn_row_pitch, float* feats, const float* lvc_attn, void* stream);
 
 /* clip/clip_surgery_model.py:127-137: ex_feats [B,C,np] (decoder features, np = h*w positions) -> ex_attn [B,np,np] =
  * softmax_j of ((cosine similarity - mean over the WHOLE batch * beta) * gamma) with negatives set to -inf.
