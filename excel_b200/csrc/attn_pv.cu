@@ -30,6 +30,17 @@
 #include "excel_b200.h"
 #include "tc.cuh"
 
+// Timing experiments (tools/attn_probe.py builds private copies of this file with -DXL_TUNING -DXL_PV_VARIANT=<mask>; the
+// product build defines neither, every XL_PV(bit) is the constant 0 and the guarded code is the plain path):
+//   1 no P V MMAs   2 no S MMAs   4 no exp / split math   8 no tcgen05.ld   16 no tcgen05.st   32 no map store
+//   64 X tiles loaded only for the first two steps   128 V tiles loaded only for the first two steps
+//   256 no MUFU.EX2   512 no lo half (P_lo = P_hi)   1024 no fp16 conversions at all   2048 Veltkamp split on the FMA pipe
+#if defined(XL_TUNING) && defined(XL_PV_VARIANT)
+#define XL_PV(bit) (((XL_PV_VARIANT) & (bit)) != 0)
+#else
+#define XL_PV(bit) false
+#endif
+
 namespace xl {
 
 namespace {
@@ -75,8 +86,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // Work item = (image, 128-row query block) walking all head groups, or -- p.gsplit, small batches -- one (image, query
     // block, head group) each, so that B * nblk * ngrp CTAs share the chip; a split item writes its partial head-sum into
     // slice g of the scratch map [ngrp][B,N,Npad] with plain stores (attn_combine_kernel adds the slices in a fixed order).
-    const int gs = p.gsplit ? ngrp : 1;
-    const int items = p.B * nblk * gs;
+    const int gsp = p.gsplit ? ngrp : 1;
+    const int items = p.B * nblk * gsp;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kXYStages; ++s) { mbar_init(&xy_full[s], 1); mbar_init(&xy_empty[s], 1); }
@@ -118,22 +129,25 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 it.kb = 0;
                 if (!p.gsplit && ++it.g < ngrp) return;
                 it.item += gridDim.x;
-                it.g = p.gsplit ? it.item % gs : 0;
+                it.g = p.gsplit ? it.item % gsp : 0;
             };
-            It ix = {(int)blockIdx.x, p.gsplit ? (int)blockIdx.x % gs : 0, 0, 0}, iv = ix;
+            It ix = {(int)blockIdx.x, p.gsplit ? (int)blockIdx.x % gsp : 0, 0, 0}, iv = ix;
             uint32_t nx = 0, nv = 0;
             while (ix.item < items || iv.item < items) {
                 if (ix.item < items) {
                     const int s = nx % kXYStages;
                     if (mbar_try(&xy_empty[s], ((nx / kXYStages) & 1) ^ 1)) {
-                        const int rb = (ix.item / gs) % nblk, b = ix.item / (gs * nblk), h = ix.g * hpi + ix.hh;
+                        const int rb = (ix.item / gsp) % nblk, b = ix.item / (gsp * nblk), h = ix.g * hpi + ix.hh;
                         uint8_t* st = xy + s * kXYStage;
                         const int xr = b * p.N + rb * 128, yr = b * p.N + ix.kb * 128;
                         const int xc = p.xo + h * 64, yc = p.yo + h * 64;
                         if (leader) {
-                            mbar_arrive_expect_tx(&xy_full[s], kXYStage);
-                            tma_load_2d(st, &tmQ, &xy_full[s], xc, xr);
-                            tma_load_2d(st + kTile, &tmQ, &xy_full[s], xc + p.lo_off, xr);
+                            const bool skip_x = XL_PV(64) && nx >= (uint32_t)kXYStages;
+                            mbar_arrive_expect_tx(&xy_full[s], skip_x ? kXYStage / 2 : kXYStage);
+                            if (!skip_x) {
+                                tma_load_2d(st, &tmQ, &xy_full[s], xc, xr);
+                                tma_load_2d(st + kTile, &tmQ, &xy_full[s], xc + p.lo_off, xr);
+                            }
                             tma_load_2d(st + 2 * kTile, &tmQ, &xy_full[s], yc, yr);
                             tma_load_2d(st + 3 * kTile, &tmQ, &xy_full[s], yc + p.lo_off, yr);
                         }
@@ -144,13 +158,17 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (iv.item < items) {
                     const int sv = nv % kVStages;
                     if (mbar_try(&v_empty[sv], ((nv / kVStages) & 1) ^ 1)) {
-                        const int b = iv.item / (gs * nblk), h = iv.g * hpi + iv.hh;
+                        const int b = iv.item / (gsp * nblk), h = iv.g * hpi + iv.hh;
                         uint8_t* vt = vs + sv * kVStage;
                         const int vr = b * p.N + iv.kb * 128, vc = p.vo + h * 64;   // V rows = keys, columns = head-dim channels
                         if (leader) {
-                            mbar_arrive_expect_tx(&v_full[sv], kVStage);
-                            tma_load_2d(vt, &tmQ, &v_full[sv], vc, vr);
-                            tma_load_2d(vt + kTile, &tmQ, &v_full[sv], vc + p.lo_off, vr);
+                            if (XL_PV(128) && nv >= (uint32_t)kVStages) {
+                                mbar_arrive(&v_full[sv]);
+                            } else {
+                                mbar_arrive_expect_tx(&v_full[sv], kVStage);
+                                tma_load_2d(vt, &tmQ, &v_full[sv], vc, vr);
+                                tma_load_2d(vt + kTile, &tmQ, &v_full[sv], vc + p.lo_off, vr);
+                            }
                         }
                         ++nv;
                         advance(iv);
@@ -169,7 +187,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t ngd = 0;
         const uint32_t xy0 = smem_u32(xy), vs0 = smem_u32(vs);
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int g_lo = p.gsplit ? item % gs : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
+            const int g_lo = p.gsplit ? item % gsp : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
             for (int g = g_lo; g < g_hi; ++g) {
                 const int hc = min(hpi, p.H - g * hpi);
                 const int U = ((nblk - 1) * 2 + nsub_last) * hc;
@@ -198,11 +216,13 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTile);
                         const uint64_t b_hi = umma_desc_sw128(yb), b_lo = umma_desc_sw128(yb + kTile);
                         if (leader) {
+                            if (!XL_PV(2)) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 umma_f16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, k != 0);
                                 umma_f16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
                                 umma_f16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
+                            }
                             }
                             if (qs.half == nsub - 1) umma_commit(&xy_empty[s]);
                             umma_commit(&s_full[gs & 3]);
@@ -223,7 +243,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     const uint64_t b_hi = umma_desc_sw128(vbox), b_lo = umma_desc_sw128(vbox + kTile);
                     const uint32_t d = tmem_o + (uint32_t)(qp.hh * 64);
                     const uint32_t first = (qp.kb | qp.half) != 0;
-                    if (leader) {
+                    if (leader && !XL_PV(1)) {
                         // keys 16k..16k+15 of the sub-tile live in its columns 16k..16k+15: hi pairs in +0..7, lo pairs in +8..15
                         if (nvalid > 48) {
 #pragma unroll
@@ -261,11 +281,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float* stg = reinterpret_cast<float*>(stg_base) + ew * 512;   // warp-private 32 rows x 16 floats
         uint32_t gl = 0, ngd = 0;                                      // load steps seen: this group's sub-tile is 2 * gl + grp
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int rb = (item / gs) % nblk, b = item / (gs * nblk);
+            const int rb = (item / gsp) % nblk, b = item / (gsp * nblk);
             const int row = rb * 128 + trow;
             const bool row_ok = row < p.N;
             const int nrow = min(32, p.N - rb * 128 - lg * 32);       // valid rows of this warp's 32 (may be <= 0)
-            const int g_lo = p.gsplit ? item % gs : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
+            const int g_lo = p.gsplit ? item % gsp : 0, g_hi = p.gsplit ? g_lo + 1 : ngrp;
             for (int g = g_lo; g < g_hi; ++g) {
                 const int hc = min(hpi, p.H - g * hpi);
                 const int zo = p.gsplit ? g * p.B + b : b;            // map slice of this item
@@ -294,13 +314,21 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             if (TAIL && key0 + c * 16 >= p.N) break;   // (uniform) padding keys only: columns unused
                             const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(buf * 64 + cq * 32 + c * 16);
                             uint32_t r[16];
-                            tmem_ld16(taddr, r);
+                            if (!XL_PV(8)) tmem_ld16(taddr, r);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 16; ++e) r[e] = 0x3c000000u + (uint32_t)(lane + e + c);
+                            }
                             if constexpr (TAIL) {
 #pragma unroll
                                 for (int e = 0; e < 16; ++e)
                                     if (key0 + c * 16 + e >= p.N) r[e] = 0xff800000u;  // -inf -> probability 0 for the padding keys
                             }
                             uint32_t ph[8], pl[8];
+                            if (XL_PV(4)) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) { ph[e] = r[2 * e]; pl[e] = r[2 * e + 1]; acc[c][2 * e] += __uint_as_float(r[e]); }
+                            } else
 #pragma unroll
                             for (int e = 0; e < 8; ++e) {
                                 // 2^10 p = exp2(alpha s - (m + log2 l - 10)): one FFMA + one MUFU per element
@@ -308,19 +336,37 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                 const float2 x = __ffma2_rn(make_float2(p.alpha, p.alpha),
                                                             make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])),
                                                             make_float2(-m_row, -m_row));
-                                const float2 v = make_float2(ex2a(x.x), ex2a(x.y));
+                                const float2 v = XL_PV(256) ? x : make_float2(ex2a(x.x), ex2a(x.y));
                                 const float2 a2 = __fadd2_rn(make_float2(acc[c][2 * e], acc[c][2 * e + 1]), v);
                                 acc[c][2 * e] = a2.x;
                                 acc[c][2 * e + 1] = a2.y;
+                                if (XL_PV(1024)) {
+                                    ph[e] = __float_as_uint(v.x); pl[e] = __float_as_uint(v.y);
+                                } else if (XL_PV(2048)) {
+                                    // Veltkamp split: hi = v rounded to 11 significant bits, computed on the FMA pipe (no fp16 -> fp32 unpack)
+                                    const float2 cc = __fmul2_rn(v, make_float2(8193.f, 8193.f));
+                                    const float2 dd = __ffma2_rn(v, make_float2(-1.f, -1.f), cc);
+                                    const float2 hf2 = __ffma2_rn(dd, make_float2(-1.f, -1.f), cc);
+                                    const float2 lo2 = __ffma2_rn(hf2, make_float2(-1.f, -1.f), v);
+                                    const __half2 hh2 = __floats2half2_rn(hf2.x, hf2.y);
+                                    const __half2 ll2 = __floats2half2_rn(lo2.x, lo2.y);
+                                    ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
+                                    pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
+                                } else {
                                 const __half2 hh2 = __floats2half2_rn(v.x, v.y);
+                                ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
+                                if (XL_PV(512)) { pl[e] = ph[e]; } else {
                                 const float2 hf2 = __half22float2(hh2);
                                 const float2 lo2 = __fadd2_rn(v, make_float2(-hf2.x, -hf2.y));
                                 const __half2 ll2 = __floats2half2_rn(lo2.x, lo2.y);
-                                ph[e] = *reinterpret_cast<const uint32_t*>(&hh2);
                                 pl[e] = *reinterpret_cast<const uint32_t*>(&ll2);
+                                }
+                                }
                             }
+                            if (!XL_PV(16)) {
                             tmem_st8(taddr, ph);       // P_hi: keys (2e, 2e+1) of the chunk in column e
                             tmem_st8(taddr + 8, pl);   // P_lo
+                            } else if (ph[0] == 0x12345678u && pl[3] == 0x9abcdef0u) acc[c][0] += 1.f;   // keep the values alive
                         }
                         };
                         if (kb == nblk - 1) chunks(std::true_type{});
@@ -333,7 +379,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
                     // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
                     // a reduce-add (performed in L2) for the others -- no thread waits on global memory.
-                    if (nrow > 0) {
+                    if (nrow > 0 && !XL_PV(32)) {
                         const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {

@@ -174,7 +174,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int trow = lg * 32 + lane;
         const float alpha = p.alpha;
         const int act = p.act;
-        const float* bias = p.bias;
         int i = 0;
         if constexpr (TMA_EPI) {
             // Per 32-column chunk each thread pulls its row slice out of TMEM, applies alpha / bias / QuickGELU /
@@ -216,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int m0, n0, z1, z2;
                 decode(t, m0, n0, z1, z2);
                 const int buf = i & 1;
+                const float* bias = p.bias ? p.bias + (int64_t)z1 * p.bias1 : nullptr;
                 mbar_wait(&acc_full[buf], (i >> 1) & 1);
                 tc_fence_after();
 #pragma unroll 1
@@ -317,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const int64_t zoffc = (int64_t)z1 * p.c1 + (int64_t)z2 * p.c2;
             const int64_t zoffs = (int64_t)z1 * p.cs1 + (int64_t)z2 * p.cs2;
+            const float* bias = p.bias ? p.bias + (int64_t)z1 * p.bias1 : nullptr;
 #pragma unroll 1
             for (int c = 0; c < kBN / 32; ++c) {
                 uint32_t r[32];
@@ -463,6 +464,16 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
     return check_launch("gemm_tc_kernel");
 }
 
+// Tile width of a [M, N] x batch GEMM: the widest tile (least L2 -> SM operand traffic per MMA) that still gives every SM a
+// tile; small problems (the per-image loops of the drop-in surface: M = one image's tokens) fall back to narrower tiles.
+int tc_pick_bn(int64_t M, int N, int batch) {
+    const int64_t mt = ceil_div64(M, kBM) * batch;
+    if (N <= 64) return 64;
+    if (N % 256 == 0 && mt * (N / 256) >= kNumSMs) return 256;
+    if (mt * ceil_div(N, 128) >= (kNumSMs * 2) / 3) return 128;
+    return 64;
+}
+
 int split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, __half* out, cudaStream_t st, float scale) {
     XL_REQUIRE(rows >= 0 && cols >= 0 && Kp >= cols && Kp % 64 == 0, "split_f16: bad shape");
     if (rows == 0) return 0;
@@ -501,4 +512,25 @@ extern "C" int excel_gemm_tc(const float* A, const float* B, float* C, const flo
     p.M = M; p.N = N; p.kblocks = Kp / 64; p.a_lo_off = Kp; p.b_lo_off = Kp; p.nb2 = 1;
     p.C = C; p.ldc = ldc; p.bias = bias; p.residual = residual; p.alpha = alpha; p.act = act;
     return tc_gemm(tmA, tmB, p, 1, bn, st);
+}
+
+// Batched GEMM on operands that are ALREADY in the engine's split-fp16 format (include/excel_b200.h).
+extern "C" int excel_gemm_tc_split(const void* As, int64_t lda, int a_lo_off, int64_t a_rows_z, const void* Bs, int64_t ldb,
+                                   int b_lo_off, int64_t b_rows_z, float* C, int64_t ldc, int64_t c_z, void* Cs, int64_t lds,
+                                   int cs_lo_off, int64_t cs_z, const float* bias, int64_t bias_z, int M, int N, int K, int batch,
+                                   float alpha, int act, void* stream) {
+    XL_REQUIRE(M >= 1 && N >= 1 && K >= 64 && K % 64 == 0 && batch >= 1, "gemm_tc_split: bad shape M=%d N=%d K=%d batch=%d (K %% 64 == 0)", M, N, K, batch);
+    XL_REQUIRE(As && Bs && lda % 8 == 0 && ldb % 8 == 0 && (reinterpret_cast<uintptr_t>(As) & 15) == 0 && (reinterpret_cast<uintptr_t>(Bs) & 15) == 0,
+               "gemm_tc_split: operands must be 16 B-aligned with row pitches that are multiples of 8 halves");
+    XL_REQUIRE(a_rows_z * (batch - 1) + M < (1ll << 31) && b_rows_z * (batch - 1) + N < (1ll << 31), "gemm_tc_split: too many rows");
+    const int bn = tc_pick_bn(M, N, batch);
+    CUtensorMap tmA, tmB;
+    if (int e = make_operand_map(&tmA, As, a_rows_z * (batch - 1) + M, a_lo_off + K, lda, 128)) return e;
+    if (int e = make_operand_map(&tmB, Bs, b_rows_z * (batch - 1) + N, b_lo_off + K, ldb, bn == 64 ? 64 : 128)) return e;
+    TcParams p = {};
+    p.M = M; p.N = N; p.kblocks = K / 64; p.a_lo_off = a_lo_off; p.b_lo_off = b_lo_off; p.nb2 = 1;
+    p.a_row1 = (int)a_rows_z; p.b_row1 = (int)b_rows_z;
+    p.C = C; p.ldc = ldc; p.c1 = c_z; p.bias = bias; p.bias1 = bias_z; p.alpha = alpha; p.act = act;
+    p.Cs = reinterpret_cast<__half*>(Cs); p.lds = lds; p.cs1 = cs_z; p.cs_lo_off = cs_lo_off;
+    return tc_gemm(tmA, tmB, p, batch, bn, (cudaStream_t)stream);
 }

@@ -18,7 +18,8 @@ struct TcParams {
     int b_row0, b_row1, b_row2, b_col0, b_col1, b_col2;
     float* C;                   // fp32 output (may be null)
     int64_t ldc, c1, c2;
-    const float* bias;          // [N] or null
+    const float* bias;          // [N] or null; batch z1 uses bias + z1 * bias1
+    int64_t bias1;
     const float* residual;      // same layout as C, or null (may alias C)
     float alpha;
     int act;                    // 0 none, 1 QuickGELU
@@ -33,6 +34,7 @@ struct TcParams {
 // box_rows = 128 for an A operand, = the tile N (64 or 128) for a B operand
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols_total, int64_t ld_elems, int box_rows);
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st);
+int tc_pick_bn(int64_t M, int N, int batch);   // tile width (64 / 128 / 256) by tile count
 // x [rows, cols] fp32 (pitch ldx) -> out [rows, 2*Kp] fp16 (hi | lo), zero padded; Kp % 64 == 0
 int split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, __half* out, cudaStream_t st, float scale = 1.f);
 

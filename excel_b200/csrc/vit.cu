@@ -174,15 +174,6 @@ static int layernorm(const Ctx& c, const float* x, const float* w, const float* 
     return check_launch("layernorm_kernel");
 }
 
-// Tile width of a [M, Nout] GEMM: the widest tile (least L2 -> SM operand traffic per MMA) that still gives every SM a tile;
-// small batches (the per-image loops of the drop-in surface: M = N tokens) fall back to narrower tiles.
-static int pick_bn(int64_t M, int Nout, int batch = 1) {
-    const int64_t mt = ceil_div64(M, 128) * batch;
-    if (Nout % 256 == 0 && mt * (Nout / 256) >= kNumSMs) return 256;
-    if (mt * ceil_div(Nout, 128) >= (kNumSMs * 2) / 3 || Nout <= 64) return Nout <= 64 ? 64 : 128;
-    return 64;
-}
-
 // A weight matrix in the engine's operand format: split fp16 [out, 2 K] (hi | lo) of  wscale * W  (wscale: the power of two
 // chosen at load time that puts max|W| at 2^13..2^14, clear of fp16's subnormal range; folded back through alpha).
 struct Wt { const void* ws; float scale; };
@@ -196,7 +187,7 @@ static int linear(const Ctx& c, const CUtensorMap& ma, Wt w, int K, int Nout, co
     p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f / w.scale; p.act = act;
     p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
     if (batch > 1) { p.a_row1 = (int)c.BN; p.c1 = c1; }
-    const int bn = pick_bn(c.BN, Nout, batch);
+    const int bn = tc_pick_bn(c.BN, Nout, batch);
     CUtensorMap mw;
     if (int e = make_operand_map(&mw, w.ws, Nout, 2 * K, 2 * K, bn == 64 ? 64 : 128)) return e;
     return tc_gemm(ma, mw, p, batch, bn, c.st);
@@ -374,7 +365,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
                 p.M = N; p.N = D; p.kblocks = np / 64; p.a_lo_off = np; p.nb2 = 1;
                 p.a_row1 = N; p.b_mn = 1; p.b_row1 = N; p.b_col0 = 2 * D; p.b_lo_off = 3 * D; p.alpha = 1.f / kProbScale;
                 p.Cs = c.w.o2; p.lds = 2 * D; p.cs1 = (int64_t)N * 2 * D; p.cs_lo_off = D;
-                if (int e = tc_gemm(c.m.pn, c.m.qkv_v, p, B, pick_bn(N, D, B), st)) return e;
+                if (int e = tc_gemm(c.m.pn, c.m.qkv_v, p, B, tc_pick_bn(N, D, B), st)) return e;
             }
             // original path: softmax(q k^T); returned attention = head SUM (:101-102,154)
             if (int e = attention_qk(c, scale, attn_l, 1.f)) return e;          // x_ori = attn_ori @ v

@@ -215,6 +215,18 @@ int excel_sgemm(const float* A, const float* B, float* C, const float* bias, con
 int excel_gemm_tc(const float* A, const float* B, float* C, const float* bias, const float* residual, int M, int N, int K,
                   int64_t lda, int64_t ldb, int64_t ldc, float alpha, int act, void* ws, int64_t ws_bytes, void* stream);
 
+/* Batched GEMM on the tcgen05 engine with operands ALREADY in its split-fp16 format (weights split once at load time by
+ * excel_split_f16, activations written in split form by a previous call) -- the decoder-side MLPs of
+ * model/segformer_head.py:18-26,66-77 at inference:
+ *   for z < batch:  D[z] = act(alpha * A[z] B[z]^T + bias[z])        act: 0 none, 1 QuickGELU, 2 ReLU
+ *   A[z] = rows z*a_rows_z .. +M of As (row pitch lda halves; hi at column 0, lo at column a_lo_off), M x K
+ *   B[z] = rows z*b_rows_z .. +N of Bs (row pitch ldb halves; hi at 0, lo at b_lo_off), N x K  (nn.Linear layout [out, in])
+ *   output: fp32 C + z*c_z (row pitch ldc floats)  OR  split fp16 Cs + z*cs_z halves (row pitch lds; lo cs_lo_off after hi)
+ *   -- exactly one of C / Cs; bias + z*bias_z ([N] floats each) or NULL.  K % 64 == 0. */
+int excel_gemm_tc_split(const void* As, int64_t lda, int a_lo_off, int64_t a_rows_z, const void* Bs, int64_t ldb, int b_lo_off,
+                        int64_t b_rows_z, float* C, int64_t ldc, int64_t c_z, void* Cs, int64_t lds, int cs_lo_off, int64_t cs_z,
+                        const float* bias, int64_t bias_z, int M, int N, int K, int batch, float alpha, int act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
