@@ -44,6 +44,8 @@ SIGNATURES = {
     "excel_row_l2_normalize": ([_p, _i, _i, _p, _p], _i),
     "excel_gemm_tc": ([_p, _p, _p, _p, _p, _i, _i, _i, _i64, _i64, _i64, _f, _i, _p, _i64, _p], _i),
     "excel_gemm_tc_split": ([_p, _i64, _i, _i64, _p, _i64, _i, _i64, _p, _i64, _i64, _p, _i64, _i, _i64, _p, _i64, _i, _i, _i, _i, _f, _i, _p], _i),
+    "excel_seg_accumulate": ([_p, _i, _i, _i, _i, _p, _i, _i, _i, _f, _p], _i),
+    "excel_seg_argmax": ([_p, _i, _i, _i, _i, _i, _p, _p], _i),
     "excel_radius_mask": ([_i, _i, _i, _p, _p], _i),
     "excel_affinity_label": ([_p, _i, _i, _i, _i, _i, _p, _i64, _p, _p], _i),
     "excel_lam_to_label": ([_p, _p, _i, _i, _i, _i, _f, _f, _f, _i, _i64, _p, _p, _p], _i),

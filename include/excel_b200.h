@@ -98,6 +98,19 @@ int excel_svc_propagate(const float* A, const float* r, const float* c, const in
 int excel_svc_cams_to_planes(const float* refined, int Q, int gh, int gw, const int* plane_off_dev, int B, int H,
                              int W, float* minmax_ws, float* planes, void* stream);
 
+/* ---------------------------------------------------------------- seg inference (tools/infer_seg_voc.py) */
+
+/* tools/infer_seg_voc.py:66-83, one scale of the multi-scale + flip loop: seg [2,C,gh,gw] = model(cat[x, flip(x)])[0].
+ *   s = bilinear(seg[0] -> h x w)                                  (flip_merge = 0: the base scale, :69-72)
+ *   s = (bilinear(seg[0]) + flip_x(bilinear(seg[1]))) / 2          (flip_merge = 1: the other scales, :78-80)
+ *   acc [C,h,w] = ((first ? 0 : acc) + s) * out_scale              (out_scale = 1/n_scales on the last call: the mean of :83)
+ * bilinear = F.interpolate(mode='bilinear', align_corners=False). */
+int excel_seg_accumulate(const float* seg, int C, int gh, int gw, int flip_merge, float* acc, int h, int w, int first,
+                         float out_scale, void* stream);
+
+/* tools/infer_seg_voc.py:85-86: labels [H,W] int64 = argmax_c bilinear(acc [C,h,w] -> H x W) (first maximum wins). */
+int excel_seg_argmax(const float* acc, int C, int h, int w, int H, int W, int64_t* labels, void* stream);
+
 /* ---------------------------------------------------------------- CAM (clip/clip.py) ---------- */
 
 /* clip/clip.py:353 (generate_clip_fts): out = tok / ||tok||_2 over the TOKEN axis, per (b, channel).

@@ -217,6 +217,19 @@ def attn_pred(attn_fts, beta=1.0, gamma=3.0):
     return torch.sigmoid((a - torch.mean(a) * beta) * gamma)
 
 
+def merge_scales(seg_list, size, label_size=None):
+    """tools/infer_seg_voc.py:66-86 given the per-scale model outputs: seg_list[0] = base scale ([2,C,g,g], only the
+    un-flipped half is used, :69-72), the others are flip-merged (:78-80); mean over scales (:83), resize to the label
+    size and argmax (:85-86).  Returns (segs [1,C,h,w], labels [1,H,W])."""
+    out = []
+    for i, segs in enumerate(seg_list):
+        up = F.interpolate(segs.float(), size=size, mode="bilinear", align_corners=False)
+        out.append(up[0].unsqueeze(0) if i == 0 else (up[:1] + up[1:].flip(-1)) / 2)
+    segs = torch.mean(torch.stack(out, dim=0), dim=0)
+    resized = F.interpolate(segs, size=size if label_size is None else label_size, mode="bilinear", align_corners=False)
+    return segs, torch.argmax(resized, dim=1)
+
+
 # --------------------------------------------------------------------------- attribute bank (a10)
 
 
