@@ -262,9 +262,14 @@ def parity_record(hp, dev, imgs_dev, cls_host, ref):
             d["hard_mismatch_px_strict"] += strict
     rec.update(e2e)
     rec["tail_on_oracle_cams"] = iso
+    from oracle.parity import svc_self_noise
+    rec["oracle_fp32_vs_fp64_plane_max_abs"] = max(svc_self_noise(ref["attr_maps_raw"][b], ref["attn_weights"][:, b], cls_host[b], (SIZE, SIZE))
+                                                   for b in range(n))
     rec["note"] = ("label_mismatch_px: GPU vs oracle labels; hard = oracle top-2 margin > 1e-5 + what the measured PAR-input "
                    "difference (plane_max_abs) can move an output (oracle/parity.py); _strict = margin 1e-5 alone; "
-                   "tail_on_oracle_cams = GPU SVC+PAR+argmax fed with the oracle's CAMs and attention")
+                   "tail_on_oracle_cams = GPU SVC+PAR+argmax fed with the oracle's CAMs and attention; "
+                   "oracle_fp32_vs_fp64_plane_max_abs = the reference's OWN fp32 rounding noise on these PAR input planes (random-init "
+                   "weights give nearly uniform attention, the per-class min-max of utils/affutils.py:69-78 amplifies it): the floor for plane_max_abs")
     return rec
 
 
@@ -387,6 +392,21 @@ def run_dropin(args):
         results[size] = dict(value=world * BATCH * args.steps / (ms / 1e3), ms_per_step=ms / args.steps, launches=int(launches),
                              clocks=clocks)
         assert last.shape == (1, size, size)
+    # f4 (decoder-side inference) timed on the batched call the seg-eval scripts make: model(inputs) for 16 images of 512^2
+    from excel_b200 import decoder
+    from excel_b200.encoder import generate_clip_fts
+    imgs16 = synthetic_batch(10 + 3 * rank)[0].to(dev)
+    with torch.no_grad():
+        ms_model = event_ms(lambda: model(imgs16), warm=2, rep=3)
+        _, _, feats16 = generate_clip_fts(imgs16, model.encoder)
+        Lf, Bf, Nf, Df = feats16.shape
+        ms_head = event_ms(lambda: decoder.segformer_head_tokens(model.decoder_fts_fuse, feats16.reshape(Lf, Bf * Nf, Df)), warm=2, rep=3)
+        fts = torch.randn(Bf, 256, SIZE // 16, SIZE // 16, device=dev)
+        ms_pred = event_ms(lambda: decoder.attn_pred(fts), warm=2, rep=3)
+    f4 = {"model_forward_ms": ms_model, "images": BATCH, "size": SIZE, "segformer_head_ms": ms_head, "attn_pred_ms": ms_pred,
+          "segformer_head_tflops_fp32_equiv": 2.0 * Bf * Nf * (12 * (Df * 256 + 256 * 256) + 12 * 256 * 256) / (ms_head * 1e-3) / 1e12,
+          "note": "ExCEL_model.forward at inference through install(): encoder + CAM + SegFormerHead (4 launches: split, 2 batched GEMMs, "
+                  "fuse GEMM) + attn_pred; the stand-in decoder of tests/dropin_tree is a 1x1 conv"}
     inst.uninstall(originals)
     r = results[SIZE]
     line = {"metric": METRIC, "value": r["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -400,7 +420,8 @@ def run_dropin(args):
                     "d2h_bytes_per_step": BATCH * SIZE * SIZE * 8, "ms_per_step": r["ms_per_step"],
                     "note": "this surface is end to end by construction: host images in, host labels out, per image"},
             "gpu_launches": r["launches"], "clocks": r["clocks"],
-            "dropin_320": {"value": results[320]["value"], "unit": "images/s", "ms_per_16_images": results[320]["ms_per_step"]}}
+            "dropin_320": {"value": results[320]["value"], "unit": "images/s", "ms_per_16_images": results[320]["ms_per_step"]},
+            "f4": f4}
     if rank == 0:
         print(json.dumps(line), flush=True)
     job.close()

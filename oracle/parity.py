@@ -25,3 +25,24 @@ def label_parity(ref_planes, lab_ref, lab_gpu, plane_err=0.0, iters=20):
     margin = (top2[0] - top2[1]) / top2[0].abs().clamp_min(1e-30)
     tol = MARGIN + 2.0 * plane_err * (1.01 ** iters) / top2[0].abs().clamp_min(1e-30)
     return int((bad & (margin > tol)).sum()), int(bad.sum())
+
+
+def svc_self_noise(attr_map, attn_weights, cls_label, size, caa_thre=0.79):
+    """How well is the REFERENCE itself defined on these inputs?  Max-abs difference of the PAR input planes (SVC ->
+    per-class min-max -> bilinear up-sampling, utils/affutils.py:177-223,55-78) between the oracle's fp32 arithmetic and
+    the same algorithm carried in float64.  With nearly uniform attention (random-init weights) the refined maps are nearly
+    constant and the reference's per-class min-max amplifies its own fp32 rounding noise: this number is the floor below
+    which no fp32 implementation can agree with another."""
+    from . import port
+    h, w = size
+    gh, gw = h // 16, w // 16
+    T32 = port.compute_trans_mat(port.svc_attention(attn_weights)).float()
+    T64 = port.compute_trans_mat(port.svc_attention(attn_weights.double()))
+    worst = 0.0
+    for c in torch.where(cls_label)[0]:
+        cam = attr_map[:, c].float()
+        mask = torch.from_numpy(port.box_mask_cv2(cam.numpy().reshape(gh, gw), caa_thre)).reshape(1, -1)
+        r32 = ((T32 * mask) @ cam.reshape(-1, 1)).reshape(gh, gw)
+        r64 = ((T64 * mask.double()) @ cam.double().reshape(-1, 1)).reshape(gh, gw)
+        worst = max(worst, (port.scale_cam(r32, (h, w)).double() - port.scale_cam(r64, (h, w))).abs().max().item())
+    return worst
