@@ -35,10 +35,24 @@
 //   1 no P V MMAs   2 no S MMAs   4 no exp / split math   8 no tcgen05.ld   16 no tcgen05.st   32 no map store
 //   64 X tiles loaded only for the first two steps   128 V tiles loaded only for the first two steps
 //   256 no MUFU.EX2   512 no lo half (P_lo = P_hi)   1024 no fp16 conversions at all   2048 Veltkamp split on the FMA pipe
+//   4096 clock trace of CTA 0 (MMA warp + one epilogue warp per group) into g_pv_trace, read back by excel_dev_pv_trace
+// (variants whose P is garbage / NaN also change the chip's POWER draw and with it the clocks of every other kernel: under
+//  the board power cap only variants that keep the data finite are valid timing comparisons)
 #if defined(XL_TUNING) && defined(XL_PV_VARIANT)
 #define XL_PV(bit) (((XL_PV_VARIANT) & (bit)) != 0)
 #else
 #define XL_PV(bit) false
+#endif
+
+#if defined(XL_TUNING)
+// timing trace (dev builds only): CTA 0 records SM clock stamps of its MMA warp and of two epilogue warps (one per group)
+__device__ unsigned long long g_pv_trace[3 * 4096];
+#define XL_TRACE(tag) do { if (XL_PV(4096) && blockIdx.x == 0 && lane == 0 && tpos < tend) g_pv_trace[tpos++] = ((unsigned long long)(tag) << 56) | ((unsigned long long)clock64() & 0xffffffffffffffull); } while (0)
+extern "C" int excel_dev_pv_trace(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_pv_trace, sizeof(g_pv_trace));
+}
+#else
+#define XL_TRACE(tag) do { } while (0)
 #endif
 
 namespace xl {
@@ -181,6 +195,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // up to four sub-steps ahead of the P V products: S(0..3), PV(0), S(4), PV(1), S(5), ...  tcgen05.mma executes in
         // issue order, so S(u+4) may overwrite the buffer PV(u) reads its P from without a further barrier.
         const bool leader = elect_one_sync();
+        int tpos = 0; const int tend = 4096; (void)tpos; (void)tend;
         struct Sub { int kb, hh, half; };             // position inside a head group
         uint32_t gs = 0, gp = 0;          // sub-steps issued (S / PV), across items: buffer = count & 3
         uint32_t ls = 0, lp = 0;          // load steps consumed (S / PV): ring stages and phases
@@ -206,8 +221,10 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const int nsub = qs.kb < nblk - 1 ? 2 : nsub_last;
                         const uint32_t s = ls % kXYStages;
                         if (qs.half == 0) {
+                            XL_TRACE(1);
                             mbar_wait(&xy_full[s], (ls / kXYStages) & 1);
                             tc_fence_after();
+                            XL_TRACE(2);
                         }
                         const int nvalid = min(64, p.N - qs.kb * 128 - qs.half * 64);   // may be <= 0: a 16-wide dummy tile
                         const uint32_t idesc = make_idesc(nvalid > 0 ? (nvalid + 15) & ~15 : 16);
@@ -227,14 +244,18 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             if (qs.half == nsub - 1) umma_commit(&xy_empty[s]);
                             umma_commit(&s_full[gs & 3]);
                         }
+                        XL_TRACE(3);
                         if (qs.half == nsub - 1) ++ls;
                         next(qs);
                     }
                     // ---- PV(up): O_hh += P[64 keys] V_hh
                     const int nsub = qp.kb < nblk - 1 ? 2 : nsub_last;
                     const uint32_t buf = gp & 3, sv = lp % kVStages;
+                    XL_TRACE(4);
                     mbar_wait(&p_ready[buf], (gp >> 2) & 1);
+                    XL_TRACE(5);
                     if (qp.half == 0) mbar_wait(&v_full[sv], (lp / kVStages) & 1);
+                    XL_TRACE(6);
                     if (up == 0) mbar_wait(o_empty, (ngd & 1) ^ 1);   // the previous group's O has been read out
                     tc_fence_after();
                     const int nvalid = min(64, p.N - qp.kb * 128 - qp.half * 64);
@@ -261,6 +282,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         }
                     }
                     if (leader && qp.half == nsub - 1) umma_commit(&v_empty[sv]);
+                    XL_TRACE(7);
                     if (qp.half == nsub - 1) ++lp;
                     ++gp;
                     next(qp);
@@ -280,6 +302,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t lane_addr = (uint32_t)(lg * 32) << 16;
         float* stg = reinterpret_cast<float*>(stg_base) + ew * 512;   // warp-private 32 rows x 16 floats
         uint32_t gl = 0, ngd = 0;                                      // load steps seen: this group's sub-tile is 2 * gl + grp
+        int tpos = ew == 0 ? 4096 : 8192; const int tend = (ew == 0 || ew == 8) ? tpos + 4096 : 0; (void)tpos; (void)tend;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int rb = (item / gsp) % nblk, b = item / (gsp * nblk);
             const int row = rb * 128 + trow;
@@ -302,8 +325,10 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         const float m_row = m_next;
                         if (row_ok && hh + 1 < hc) m_next = __ldg(mrow + (int64_t)(hh + 1) * p.N);
                         const uint32_t u = 2 * gl + grp, buf = u & 3;
+                        XL_TRACE(8);
                         mbar_wait(&s_full[buf], (u >> 2) & 1);
                         tc_fence_after();
+                        XL_TRACE(9);
                         // Only the LAST key block of an image can hold padding keys.  The two cases are separate instantiations of the
                         // chunk code: written as one body, the per-element `key >= N ? -inf : s` test was if-converted and ran
                         // (ISETP + SEL per element, a quarter of the epilogue's instructions) for every key block.
@@ -371,14 +396,17 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         };
                         if (kb == nblk - 1) chunks(std::true_type{});
                         else chunks(std::false_type{});
+                        XL_TRACE(10);
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&p_ready[buf]);
+                        XL_TRACE(11);
                     }
                     // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
                     // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
                     // a reduce-add (performed in L2) for the others -- no thread waits on global memory.
+                    XL_TRACE(12);
                     if (nrow > 0 && !XL_PV(32)) {
                         const float cf = p.coef * (1.f / 1024.f);
 #pragma unroll
@@ -398,8 +426,10 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                 else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
                                 tma_store_commit();
                             }
+                            XL_TRACE(13);
                         }
                     }
+                    XL_TRACE(14);
                 }
                 if (lane == 0) tma_store_wait_all<0>();   // this group's map blocks are performed before the next group adds to them
                 // ---- O of head hh = qt of the group: TMEM -> split fp16 -> o[b*N + row, h*64 ..] (hi) / [.. + D] (lo)

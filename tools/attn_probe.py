@@ -47,6 +47,14 @@ def run_one(mask, B, S):
     b.record()
     torch.cuda.synchronize()
     print(json.dumps({"mask": mask, "B": B, "S": S, "encoder_ms": round(a.elapsed_time(b) / 5, 3)}), flush=True)
+    if mask & 4096:   # clock trace of the LAST attn_pv launch (CTA 0): dump for offline analysis
+        import ctypes
+        import numpy as np
+        buf = np.zeros(3 * 4096, dtype=np.uint64)
+        L = _lib.lib()
+        L.excel_dev_pv_trace.argtypes, L.excel_dev_pv_trace.restype = [ctypes.c_void_p], ctypes.c_int
+        assert L.excel_dev_pv_trace(buf.ctypes.data) == 0
+        np.save(os.path.join(ROOT, "gpurun_out", f"pv_trace_{mask}.npy"), buf)
 
 
 if __name__ == "__main__":
