@@ -22,8 +22,8 @@ SIGNATURES = {
     "excel_device_arch": ([_i], _i),
     "excel_launch_count": ([], _i64),
     "excel_confusion_hist": ([_p, _p, _i64, _i, _p, _p], _i),
-    "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p], _i),
-    "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p], _i),
+    "excel_par_forward": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _i, _p, _i, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p], _i),
+    "excel_par_labels": ([_p, _p, _p, _p, _i, _i, _i, _p, _p], _i),
     "excel_svc_mean_attention": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p], _i),
     "excel_svc_seg_attention": ([_p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p, _p, _p], _i),
     "excel_svc_sinkhorn": ([_p, _i, _i, _i, _p, _p, _p], _i),
@@ -133,6 +133,49 @@ def on_tensor_device(fn):
 def f32c(t):
     """fp32 + contiguous, like the reference's `.float()` calls (no copy when already so)."""
     return t.detach().to(torch.float32).contiguous()
+
+
+class _PinnedRing:
+    """Small ring of pinned host staging buffers per device: index arrays (a few hundred bytes per call) go to the device
+    as ONE asynchronous copy from pinned memory instead of several blocking copies from pageable memory.  A slot is reused
+    only after the copy that last read it has completed (event)."""
+
+    def __init__(self, slots=8):
+        self.slots = [None] * slots
+        self.i = 0
+
+    def upload(self, arr, dev):
+        """arr: 1-D numpy int32 / int64 array -> device tensor (same dtype); asynchronous on the current stream."""
+        import numpy as np
+        t_dtype = torch.int32 if arr.dtype == np.int32 else torch.int64
+        k = self.i % len(self.slots)
+        self.i += 1
+        slot = self.slots[k]
+        nbytes = max(int(arr.nbytes), 8)
+        if slot is None or slot[0].numel() < nbytes:
+            slot = [torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory(), None]
+            self.slots[k] = slot
+        elif slot[1] is not None:
+            slot[1].synchronize()
+        host = slot[0][:arr.nbytes].view(t_dtype)
+        host.copy_(torch.from_numpy(arr))
+        out = torch.empty(arr.shape[0], dtype=t_dtype, device=dev)
+        out.copy_(host, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(dev))
+        return out
+
+
+_RINGS = {}
+
+
+def upload_ints(arr, dev):
+    dev = torch.device(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ring = _RINGS.get(key)
+    if ring is None:
+        ring = _RINGS[key] = _PinnedRing()
+    return ring.upload(arr, dev)
 
 
 def int_array(values):

@@ -23,7 +23,7 @@ def _class_lists(cls_labels):
     return [torch.where(row)[0].to(torch.int64) for row in host]
 
 
-def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None, seg_attn=None):
+def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, order=None, seg_attn=None, pair_index=None):
     """attr_maps [B,n_p,K]; attn [L,B,N,N] (arbitrary layer / image / row strides, columns contiguous: the encoder returns a
     view with row pitch round_up(N,4)).
     Returns refined [Q, n_p] for the Q = sum_b n_b (image, class) pairs, image-major (images in `order`, default
@@ -38,11 +38,16 @@ def _svc_vectors(attr_maps, attn, cls_lists, gh, gw, caa_thre, attn_layers, orde
     attr_maps = _f32(attr_maps)
     if attr_maps.stride(2) != 1:
         attr_maps = attr_maps.contiguous()
-    order = list(range(len(cls_lists))) if order is None else order
-    img_of = torch.tensor([b for b in order for _ in cls_lists[b]], dtype=torch.int32)
-    cls_of = torch.cat([cls_lists[b] for b in order]).to(torch.int32) if cls_lists else torch.zeros(0, dtype=torch.int32)
-    Q = int(img_of.numel())
-    img_of, cls_of = img_of.to(dev, non_blocking=True), cls_of.to(dev, non_blocking=True)
+    if pair_index is not None:        # (img_of, cls_of) int32 device views prepared by the caller (one pinned upload)
+        img_of, cls_of = pair_index
+        Q = int(img_of.numel())
+    else:
+        order = list(range(len(cls_lists))) if order is None else order
+        io = np.asarray([b for b in order for _ in cls_lists[b]], dtype=np.int32)
+        co = np.concatenate([cls_lists[b].numpy() for b in order]).astype(np.int32) if cls_lists else np.zeros(0, np.int32)
+        Q = int(io.size)
+        both = _lib.upload_ints(np.concatenate([io, co]), dev)
+        img_of, cls_of = both[:Q], both[Q:]
     st = _lib.stream()
     A = torch.empty((B, n_p, n_p), dtype=torch.float32, device=dev)
     if seg_attn is None:
@@ -110,14 +115,14 @@ def refine_cams_with_aff(attr_map, attn_weights, cls_label, size, caa_thre=0.79,
     return [o.view(h // 16, w // 16) for o in out], cls_lst
 
 
-def _cams_to_planes(refined, counts, gh, gw, H, W):
+def _cams_to_planes(refined, counts, gh, gw, H, W, plane_off_dev=None):
     """refined [Q, gh*gw] -> (planes [P,H,W], plane_off int32 [B+1] device, plane_off host list)."""
     dev = refined.device
     B = len(counts)
     off = np.zeros(B + 1, dtype=np.int32)
     off[1:] = np.cumsum([c + 1 for c in counts])
     Q, P = int(sum(counts)), int(off[-1])
-    plane_off = torch.from_numpy(off).to(dev, non_blocking=True)
+    plane_off = _lib.upload_ints(off, dev) if plane_off_dev is None else plane_off_dev
     planes = torch.empty((P, H, W), dtype=torch.float32, device=dev)
     ws = torch.empty((max(2 * Q, 1),), dtype=torch.float32, device=dev)
     _lib.call("excel_svc_cams_to_planes", _lib.ptr(refined), Q, gh, gw, _lib.ptr(plane_off), B, H, W, _lib.ptr(ws),
@@ -137,7 +142,7 @@ def refine_cams_with_bkg_weclip(cam_refined_list, inputs_denorm, cls_lst, par, s
     refined = torch.stack([_f32(c).reshape(-1) for c in cam_refined_list], 0).contiguous()
     planes, plane_off, off = _cams_to_planes(refined, [len(cam_refined_list)], gh, gw, H, W)
     dev = planes.device
-    key = torch.cat([torch.zeros(1, dtype=torch.int64), cls_lst.to(torch.int64).cpu() + 1]).to(dev)   # :168
+    key = _lib.upload_ints(np.concatenate([[0], cls_lst.to(torch.int64).cpu().numpy() + 1]).astype(np.int64), dev)   # :168
     out = par_refine_planes(inputs_denorm.unsqueeze(0), planes, plane_off, int(off[-1]), par.dilations, par.num_iter,
                             getattr(par, "group", 0), par.w1, par.w2)
     labels = par_labels(out, plane_off, key, 1)
@@ -176,19 +181,25 @@ def refine_batch(attr_maps, attn_weights, cls_labels, par_imgs, par, out_size=No
     order = list(range(B)) if return_cams else sorted(range(B), key=lambda b: counts[b])
     identity = order == list(range(B))
     counts_s = [counts[b] for b in order]
-    refined = _svc_vectors(attr_maps, attn_weights, cls_lists, gh, gw, caa_thre, attn_layers, order)
-    planes, plane_off, off = _cams_to_planes(refined, counts_s, gh, gw, H, W)
-    dev = planes.device
-    key = torch.cat([torch.cat([torch.zeros(1, dtype=torch.int64), cls_lists[b] + 1]) for b in order]).to(dev, non_blocking=True)
-    imgs_s = par_imgs if identity else par_imgs.index_select(0, torch.tensor(order, device=par_imgs.device))
+    dev = attr_maps.device
+    # every index array of the step in ONE pinned upload: (image, class) of the Q vector slots, plane offsets of the B
+    # slots, the slot -> image order; the int64 plane keys in a second one
+    io = np.asarray([b for b in order for _ in cls_lists[b]], dtype=np.int32)
+    co = np.concatenate([cls_lists[b].numpy() for b in order]).astype(np.int32)
+    off = np.zeros(B + 1, dtype=np.int32)
+    off[1:] = np.cumsum([c + 1 for c in counts_s])
+    Q = int(io.size)
+    idx = _lib.upload_ints(np.concatenate([io, co, off, np.asarray(order, dtype=np.int32)]), dev)
+    img_of, cls_of, plane_off, order_dev = idx[:Q], idx[Q:2 * Q], idx[2 * Q:2 * Q + B + 1], idx[2 * Q + B + 1:]
+    key = _lib.upload_ints(np.concatenate([np.concatenate([[0], cls_lists[b].numpy() + 1]) for b in order]).astype(np.int64), dev)
+    refined = _svc_vectors(attr_maps, attn_weights, cls_lists, gh, gw, caa_thre, attn_layers, order, pair_index=(img_of, cls_of))
+    planes, plane_off, off = _cams_to_planes(refined, counts_s, gh, gw, H, W, plane_off_dev=plane_off)
     segs = _segments([c + 1 for c in counts_s])
-    out = par_refine_planes(imgs_s, planes, plane_off, max(counts) + 1, par.dilations, par.num_iter,
-                            getattr(par, "group", 0), par.w1, par.w2, segments=segs)
-    labels = par_labels(out, plane_off, key, B)
-    if not identity:
-        unsorted = torch.empty_like(labels)
-        unsorted.index_copy_(0, torch.tensor(order, device=dev), labels)
-        labels = unsorted
+    # the PAR runs read the images through the slot -> image index (no gathered copy of the batch) and the labels land in
+    # the caller's order
+    out = par_refine_planes(par_imgs, planes, plane_off, max(counts) + 1, par.dilations, par.num_iter,
+                            getattr(par, "group", 0), par.w1, par.w2, segments=segs, img_index=None if identity else order_dev)
+    labels = par_labels(out, plane_off, key, B, out_index=None if identity else order_dev)
     if return_cams:
         return labels, planes, plane_off, refined
     return labels

@@ -26,7 +26,7 @@ struct ParGeom {
 // ------------------------------------------------------------------------------------------------
 // bilinear resize, align_corners=True (utils/PAR.py:67).  One thread per output pixel.
 __global__ void par_resize_ac_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int64_t sy,
-                                     float* __restrict__ dst, int hi, int wi, int H, int W) {
+                                     float* __restrict__ dst, int hi, int wi, int H, int W, const int* __restrict__ img_index) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int bc = blockIdx.z;  // b*3 + c
@@ -37,7 +37,7 @@ __global__ void par_resize_ac_kernel(const float* __restrict__ src, int64_t sb, 
     const int y0 = (int)fy, x0 = (int)fx;
     const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
     const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
-    const float* p = src + (int64_t)(bc / 3) * sb + (int64_t)(bc % 3) * sc;
+    const float* p = src + (int64_t)(img_index ? img_index[bc / 3] : bc / 3) * sb + (int64_t)(bc % 3) * sc;
     const float v = hy * (hx * __ldg(p + y0 * sy + x0) + lx * __ldg(p + y0 * sy + x1)) +
                     ly * (hx * __ldg(p + y1 * sy + x0) + lx * __ldg(p + y1 * sy + x1));
     dst[((int64_t)bc * H + y) * W + x] = v;
@@ -94,13 +94,15 @@ __device__ constexpr int kStdDil[6] = {1, 2, 4, 8, 12, 24};
 template <int NDIL, bool STD>
 __global__ void __launch_bounds__(256, 2)
 par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, float* __restrict__ aff,
-                    int H, int W, int Wp, int halo_rt, ParGeom g, float w1) {
+                    int H, int W, int Wp, int halo_rt, ParGeom g, float w1, const int* __restrict__ img_index) {
     constexpr int K = 8 * NDIL;
     extern __shared__ float sm[];
     const int halo = STD ? 24 : halo_rt;
     const int TW = kTX + 2 * halo, TH = kTY + 2 * halo;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY, b = blockIdx.z;
-    stage_tile_async(sm, img + (int64_t)b * sb, sc, sy, 3, x0, y0, halo, TW, TH, H, W, threadIdx.y * 32 + threadIdx.x);
+    // image slot b of the launch reads image img_index[b] of the caller's batch (runs sorted by plane count: no gather copy)
+    stage_tile_async(sm, img + (int64_t)(img_index ? img_index[b] : b) * sb, sc, sy, 3, x0, y0, halo, TW, TH, H, W,
+                     threadIdx.y * 32 + threadIdx.x);
     cp_async_wait_all();
     __syncthreads();
     const int x = x0 + threadIdx.x;
@@ -436,7 +438,8 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
 // labels[b,y,x] = key[plane_off[b] + argmax_c planes[plane_off[b]+c, y, x]]; first maximum wins and
 // NaN compares as the maximum (torch.argmax semantics).
 __global__ void par_labels_kernel(const float* __restrict__ planes, const int* __restrict__ plane_off,
-                                  const int64_t* __restrict__ key, int64_t* __restrict__ labels, int64_t hw) {
+                                  const int64_t* __restrict__ key, int64_t* __restrict__ labels, int64_t hw,
+                                  const int* __restrict__ out_index) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= hw) return;
@@ -447,7 +450,7 @@ __global__ void par_labels_kernel(const float* __restrict__ planes, const int* _
         const float v = planes[(int64_t)p * hw + i];
         if (!(best != best) && (v > best || v != v)) { best = v; arg = p; }
     }
-    labels[(int64_t)b * hw + i] = pend > pbeg ? key[arg] : 0;
+    labels[(int64_t)(out_index ? out_index[b] : b) * hw + i] = pend > pbeg ? key[arg] : 0;
 }
 
 static int make_geom(const int* dilations, int n_dil, float w1, float w2, ParGeom* g) {
@@ -506,19 +509,19 @@ static bool is_std_dilations(const ParGeom& g) {
 
 template <int NDIL>
 static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy, float* aff, int B, int H, int W,
-                           int Wp, const ParGeom& g, float w1, cudaStream_t st) {
+                           int Wp, const ParGeom& g, float w1, const int* img_index, cudaStream_t st) {
     const int halo = max_dilation(g);
     const size_t smem = tile_smem_bytes(halo, 3);
     dim3 grid(ceil_div(W, kTX), ceil_div(H, kTY), B), block(32, 8);
     if constexpr (NDIL == 6) {
         if (is_std_dilations(g)) {
             if (int e = set_smem(par_affinity_kernel<6, true>, smem, "par_affinity")) return e;
-            par_affinity_kernel<6, true><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
+            par_affinity_kernel<6, true><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index);
             return check_launch("par_affinity_kernel<std>");
         }
     }
     if (int e = set_smem(par_affinity_kernel<NDIL, false>, smem, "par_affinity")) return e;
-    par_affinity_kernel<NDIL, false><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1);
+    par_affinity_kernel<NDIL, false><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index);
     return check_launch("par_affinity_kernel");
 }
 
@@ -581,7 +584,7 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
                                  int hi, int wi, int H, int W, const int* dilations, int n_dil, float w1, float w2,
                                  int num_iter, int group, float* resize_ws, float* aff_ws, const float* planes_in,
                                  float* planes_out, float* planes_tmp, const int* plane_off_dev, int total_planes,
-                                 int max_c, void* stream) {
+                                 int max_c, const int* img_index_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ParGeom g;
     if (int e = make_geom(dilations, n_dil, w1, w2, &g)) return e;
@@ -600,10 +603,11 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         XL_REQUIRE(resize_ws != nullptr, "PAR: image %dx%d != mask %dx%d needs a resize workspace", hi, wi, H, W);
         XL_REQUIRE(B * 3 <= 65535, "PAR: B too large for the resize launch");
         dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * 3), block(32, 8);
-        par_resize_ac_kernel<<<grid, block, 0, st>>>(img, stride_b, stride_c, stride_y, resize_ws, hi, wi, H, W);
+        par_resize_ac_kernel<<<grid, block, 0, st>>>(img, stride_b, stride_c, stride_y, resize_ws, hi, wi, H, W, img_index_dev);
         if (int e = check_launch("par_resize_ac_kernel")) return e;
         img = resize_ws;
         stride_y = W; stride_c = (int64_t)H * W; stride_b = 3 * stride_c;
+        img_index_dev = nullptr;   // the resized copy is in slot order
     }
     // planes staged per pass: all of them up to 4; images with more planes run passes of 3 (measured at 512^2 x 16:
     // 5-6 planes take 8.1 ms / 20 steps in passes of 3 against 12.5 ms in passes of 4, whose half-height tiles need 2 passes too)
@@ -637,8 +641,8 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
     for (int b0 = 0; b0 < B; b0 += group) {
         const int nb = B - b0 < group ? B - b0 : group;
         int e = 0;
-        XL_NDIL_SWITCH(n_dil, e = launch_affinity<ND>(img + (int64_t)b0 * stride_b, stride_b, stride_c, stride_y,
-                                                      aff_ws, nb, H, W, Wp, g, w1, st));
+        XL_NDIL_SWITCH(n_dil, e = launch_affinity<ND>(img_index_dev ? img : img + (int64_t)b0 * stride_b, stride_b, stride_c, stride_y,
+                                                      aff_ws, nb, H, W, Wp, g, w1, img_index_dev ? img_index_dev + b0 : nullptr, st));
         if (e) return e;
         if (!iterate) {  // affinity only: aff_ws holds all B images
             aff_ws += (int64_t)nb * 8 * n_dil * H * Wp;
@@ -657,12 +661,12 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
 }
 
 extern "C" int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_t* plane_key_dev,
-                                int64_t* labels, int B, int H, int W, void* stream) {
+                                int64_t* labels, int B, int H, int W, const int* out_index_dev, void* stream) {
     XL_REQUIRE(B >= 0 && H > 0 && W > 0, "PAR labels: bad shape");
     if (B == 0) return 0;
     XL_REQUIRE(B <= 65535, "PAR labels: B=%d > 65535", B);
     const int64_t hw = (int64_t)H * W;
     dim3 grid((unsigned)ceil_div64(hw, 256), B);
-    par_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, plane_off_dev, plane_key_dev, labels, hw);
+    par_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, plane_off_dev, plane_key_dev, labels, hw, out_index_dev);
     return check_launch("par_labels_kernel");
 }

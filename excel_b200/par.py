@@ -28,16 +28,19 @@ def _side_streams(dev, n):
 
 
 @_lib.on_tensor_device
-def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2, segments=None):
+def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group=0, w1=W1, w2=W2, segments=None, img_index=None):
     """imgs [B,3,hi,wi]; planes [P,H,W] packed mask planes; plane_off int32 [B+1] (device).
-    segments: optional [(b0, b1, max planes per image)] runs of consecutive images launched separately (so that each
-    run gets the kernel variant matching its plane count).  Returns the refined planes [P,H,W] (a new tensor)."""
+    segments: optional [(b0, b1, max planes per image)] runs of consecutive SLOTS launched separately (so that each
+    run gets the kernel variant matching its plane count).  img_index: optional int32 [B] (device): slot b reads image
+    img_index[b] (the batch processed in another order without gathering the images).
+    Returns the refined planes [P,H,W] (a new tensor)."""
     _lib.ptr(imgs), _lib.ptr(planes)   # CUDA tensors only: raises for CPU inputs (no fallback)
     imgs = imgs.float()
     if imgs.stride(-1) != 1:
         imgs = imgs.contiguous()
     planes = _lib.f32c(planes)
-    B, _, hi, wi = imgs.shape
+    _, _, hi, wi = imgs.shape
+    B = plane_off.numel() - 1
     P, H, W = planes.shape
     if num_iter <= 0 or P == 0:
         return planes.clone()
@@ -61,9 +64,11 @@ def par_refine_planes(imgs, planes, plane_off, max_c, dilations, num_iter, group
         with torch.cuda.stream(st):
             aff = torch.empty((g, K, H, _pitch(W)), dtype=torch.float32, device=dev)   # internal layout: row pitch % 4 == 0
             rs = torch.empty((nb, 3, H, W), dtype=torch.float32, device=dev) if (hi, wi) != (H, W) else None
-            _lib.call("excel_par_forward", _lib.ptr(imgs) + b0 * imgs.stride(0) * 4, imgs.stride(0), imgs.stride(1),
+            img_ptr = _lib.ptr(imgs) + (0 if img_index is not None else b0 * imgs.stride(0) * 4)
+            idx_ptr = None if img_index is None else _lib.ptr(img_index) + 4 * b0
+            _lib.call("excel_par_forward", img_ptr, imgs.stride(0), imgs.stride(1),
                       imgs.stride(2), nb, hi, wi, H, W, dil, len(dilations), w1, w2, num_iter, g, _lib.ptr(rs), _lib.ptr(aff),
-                      _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off) + 4 * b0, P, int(mc), _lib.stream())
+                      _lib.ptr(planes), _lib.ptr(out), _lib.ptr(tmp), _lib.ptr(plane_off) + 4 * b0, P, int(mc), idx_ptr, _lib.stream())
     for st in side[:len(segments) - 1]:
         cur.wait_stream(st)
     return out
@@ -81,17 +86,18 @@ def par_affinity(imgs, size, dilations, w1=W1, w2=W2):
     rs = torch.empty((B, 3, H, W), dtype=torch.float32, device=imgs.device) if (hi, wi) != (H, W) else None
     _lib.call("excel_par_forward", _lib.ptr(imgs), imgs.stride(0), imgs.stride(1), imgs.stride(2), B, hi, wi, H, W,
               _lib.int_array(dilations), len(dilations), w1, w2, 0, B, _lib.ptr(rs), _lib.ptr(aff),
-              None, None, None, None, 0, 0, _lib.stream())
+              None, None, None, None, 0, 0, None, _lib.stream())
     return aff[..., :W]
 
 
 @_lib.on_tensor_device
-def par_labels(planes, plane_off, plane_key, B):
-    """utils/affutils.py:86-87: labels [B,H,W] int64 = plane_key[argmax over image b's planes]."""
+def par_labels(planes, plane_off, plane_key, B, out_index=None):
+    """utils/affutils.py:86-87: labels [B,H,W] int64 = plane_key[argmax over the planes of slot b], written to
+    labels[out_index[b]] (int32 [B], device) or labels[b]."""
     P, H, W = planes.shape
     labels = torch.empty((B, H, W), dtype=torch.int64, device=planes.device)
     _lib.call("excel_par_labels", _lib.ptr(planes), _lib.ptr(plane_off), _lib.ptr(plane_key), _lib.ptr(labels),
-              B, H, W, _lib.stream())
+              B, H, W, _lib.ptr(out_index), _lib.stream())
     return labels
 
 

@@ -43,17 +43,21 @@ int64_t excel_launch_count(void);     /* kernels this library has enqueued so fa
  *   steps stream it with TMA, whose row stride must be a multiple of 16 B).  (group = 1 keeps one 512^2 image's
  *   50 MB of affinities in the 126 MB L2 across the steps but under-fills the GPU: measured 1.8x slower than
  *   whole-batch launches, which stream the affinities from HBM at 67-95 % of its peak.)
- *   planes_out == NULL or num_iter == 0: affinity only, aff_ws must then hold [B,K,H,Wp]. */
+ *   planes_out == NULL or num_iter == 0: affinity only, aff_ws must then hold [B,K,H,Wp].
+ *   img_index_dev: NULL, or int32 [B] (device): slot b of this call (its planes are plane_off_dev[b]..) reads image
+ *   img_index_dev[b] of `img` -- lets a caller process the images of a batch in another order (e.g. sorted by plane count)
+ *   without gathering them. */
 int excel_par_forward(const float* img, int64_t stride_b, int64_t stride_c, int64_t stride_y, int B,
                       int hi, int wi, int H, int W, const int* dilations_host, int n_dil, float w1, float w2,
                       int num_iter, int group, float* resize_ws, float* aff_ws, const float* planes_in,
                       float* planes_out, float* planes_tmp, const int* plane_off_dev, int total_planes, int max_c,
-                      void* stream);
+                      const int* img_index_dev, void* stream);
 
-/* utils/affutils.py:86-87 (_refine_cams): labels[b] = plane_key[argmax_c planes of image b]
- * (first maximum wins, NaN is a maximum); labels [B,H,W] int64, plane_key_dev [P] int64. */
+/* utils/affutils.py:86-87 (_refine_cams): labels[o(b)] = plane_key[argmax_c planes of slot b]
+ * (first maximum wins, NaN is a maximum); labels [B,H,W] int64, plane_key_dev [P] int64; o(b) = out_index_dev[b]
+ * (int32 [B], device) or b when NULL. */
 int excel_par_labels(const float* planes, const int* plane_off_dev, const int64_t* plane_key_dev,
-                     int64_t* labels, int B, int H, int W, void* stream);
+                     int64_t* labels, int B, int H, int W, const int* out_index_dev, void* stream);
 
 /* ---------------------------------------------------------------- SVC (utils/affutils.py) ------ */
 
