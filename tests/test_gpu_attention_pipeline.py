@@ -105,3 +105,20 @@ def test_persistent_item_loop_more_items_than_sms():
     assert (attn.cpu()[:, pick] - attn_r).abs().max() < 5e-5
     assert (tok.cpu()[pick] - tok_r).abs().max() < 1e-4
     assert ((feats.cpu()[:, pick] - feats_r).abs().amax(dim=(1, 2, 3)) / feats_r.abs().amax(dim=(1, 2, 3))).max() < 1e-4
+
+
+@pytest.mark.parametrize("B,S", [(25, 224), (8, 320)])
+def test_split_attention_launch_plans_agree(B, S):
+    """attn_pv_plan picks the work-item shape by batch: B = 25 at 224^2 runs one item per (image, query block, group of 4
+    heads), B = 8 at 320^2 groups of 2 heads, B = 1 single heads -- each with its partial maps summed in a fixed order.
+    The plans must agree with each other (and each is checked against the oracle elsewhere) to fp32 summation order."""
+    from excel_b200.encoder import SurgeryViT, generate_clip_fts
+    enc = SurgeryViT(synth.random_visual_weights(seed=7))
+    imgs = synth.images(B, S, seed=80).cuda()
+    tok, attn, feats = generate_clip_fts(imgs, enc)
+    for i in (0, B // 2, B - 1):
+        tok1, attn1, feats1 = generate_clip_fts(imgs[i:i + 1], enc)
+        assert (attn[:, i] - attn1[:, 0]).abs().max() < 1e-5
+        assert (tok[i] - tok1[0]).abs().max() < 1e-5
+        assert ((feats[:, i] - feats1[:, 0]).abs().amax(dim=(1, 2)) / feats1[:, 0].abs().amax(dim=(1, 2))).max() < 2e-5
+    torch.cuda.synchronize()

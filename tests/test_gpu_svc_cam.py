@@ -71,7 +71,7 @@ def test_cam_golden_and_oracle(golden):
     out = clip.clip_feature_surgery(t(G["F"]).cuda(), t(G["T"]).cuda()).cpu()
     assert (out - t(G["cam"])).abs().max() < 1e-5
     g = torch.Generator().manual_seed(0)
-    for (B, N, E, T) in ((3, 197, 512, 45), (2, 785, 512, 103), (1, 50, 768, 7)):
+    for (B, N, E, T) in ((3, 197, 512, 45), (2, 785, 512, 103), (1, 50, 768, 7), (2, 401, 512, 300)):
         tok = torch.randn(B, N, E, generator=g)
         Fn = clip.token_normalize(tok.cuda())
         assert (Fn.cpu() - tok / tok.norm(dim=1, keepdim=True)).abs().max() < 1e-6
