@@ -67,7 +67,8 @@ __global__ void pos_resize_kernel(const float* __restrict__ pos, int g0, int g, 
 }
 
 // ---- LayerNorm (fp32, eps 1e-5; clip_surgery_model.py:271-277), one warp per row -----------------------
-// Optional prologue used for the embedding: row n==0 of every image takes `cls`, and `pos[n]` is added
+// 16 B loads (a lane owns 4 consecutive channels per 128-channel group), 16 B fp32 stores, 8 B stores of the split-fp16
+// halves.  Optional prologue used for the embedding: row n==0 of every image takes `cls`, and `pos[n]` is added
 // before normalising (x = ln_pre(cat(cls, patches) + pos), :424-438).
 template <bool EMBED>
 __global__ void __launch_bounds__(256)
@@ -81,36 +82,55 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     float* yr = y ? y + row * D : nullptr;
     __half* sr = ys ? ys + row * 2 * D : nullptr;  // split-fp16 copy (operand of the next GEMM): hi | lo, D apart
     const int n = EMBED ? (int)(row % N) : 0;
-    constexpr int MAXV = 32;  // D <= 1024
-    float v[MAXV];
+    constexpr int MAXV = 8;  // D <= 1024, D % 4 == 0
+    float4 v[MAXV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int d = lane + 32 * i;
-        float t = 0.f;
+        const int d = 4 * (lane + 32 * i);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (d < D) {
-            t = xr[d];
-            if (EMBED) t = (n == 0 ? cls[d] : t) + pos[(int64_t)n * D + d];
+            t = *reinterpret_cast<const float4*>(xr + d);
+            if (EMBED) {
+                if (n == 0) t = *reinterpret_cast<const float4*>(cls + d);
+                const float4 pp = *reinterpret_cast<const float4*>(pos + (int64_t)n * D + d);
+                t.x += pp.x; t.y += pp.y; t.z += pp.z; t.w += pp.w;
+            }
         }
         v[i] = t;
-        s += t;
+        s += (t.x + t.y) + (t.z + t.w);
     }
     const float mean = warp_sum(s) / (float)D;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int d = lane + 32 * i;
-        const float t = d < D ? v[i] - mean : 0.f;
-        q = fmaf(t, t, q);
+        if (4 * (lane + 32 * i) < D) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+            q = fmaf(a, a, q); q = fmaf(b, b, q); q = fmaf(c, c, q); q = fmaf(e, e, q);
+        }
     }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int d = lane + 32 * i;
+        const int d = 4 * (lane + 32 * i);
         if (d < D) {
-            const float o = (v[i] - mean) * rstd * w[d] + bvec[d];
-            if (yr) yr[d] = o;
-            if (sr) split_store(sr + d, sr + D + d, o);
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + d)), bb = __ldg(reinterpret_cast<const float4*>(bvec + d));
+            const float4 o = make_float4((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
+                                         (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+            if (yr) *reinterpret_cast<float4*>(yr + d) = o;
+            if (sr) {
+                // hi saturates at fp16's largest finite value (|v| up to 2 x 65504 stays finite), lo = v - hi
+                const float c0 = fminf(fmaxf(o.x, -65504.f), 65504.f), c1 = fminf(fmaxf(o.y, -65504.f), 65504.f);
+                const float c2 = fminf(fmaxf(o.z, -65504.f), 65504.f), c3 = fminf(fmaxf(o.w, -65504.f), 65504.f);
+                __align__(8) __half2 h[2], l[2];
+                h[0] = __floats2half2_rn(c0, c1);
+                h[1] = __floats2half2_rn(c2, c3);
+                const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]);
+                l[0] = __floats2half2_rn(o.x - f0.x, o.y - f0.y);
+                l[1] = __floats2half2_rn(o.z - f1.x, o.w - f1.y);
+                *reinterpret_cast<uint2*>(sr + d) = *reinterpret_cast<const uint2*>(h);
+                *reinterpret_cast<uint2*>(sr + D + d) = *reinterpret_cast<const uint2*>(l);
+            }
         }
     }
 }
