@@ -464,14 +464,23 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
     return check_launch("gemm_tc_kernel");
 }
 
-// Tile width of a [M, N] x batch GEMM: the widest tile (least L2 -> SM operand traffic per MMA) that still gives every SM a
-// tile; small problems (the per-image loops of the drop-in surface: M = one image's tokens) fall back to narrower tiles.
+// Tile width of a [M, N] x batch GEMM on 148 persistent CTAs: minimise  waves(bn) x (bn + 64)  -- the time of a tile grows
+// with its width plus the fixed cost of streaming the A rows -- over the widths the shape allows; ties go to the wider tile
+// (least L2 -> SM operand traffic per MMA).  Large batches end up on 256-wide tiles; the per-image loops of the drop-in
+// surface (M = one image's tokens: 9 row tiles) get one full wave of narrow tiles for the N = 768 layers and a single wave
+// of 256-wide tiles for in_proj / c_fc instead of two waves of 128-wide ones.
 int tc_pick_bn(int64_t M, int N, int batch) {
-    const int64_t mt = ceil_div64(M, kBM) * batch;
     if (N <= 64) return 64;
-    if (N % 256 == 0 && mt * (N / 256) >= kNumSMs) return 256;
-    if (mt * ceil_div(N, 128) >= (kNumSMs * 2) / 3) return 128;
-    return 64;
+    const int64_t mt = ceil_div64(M, kBM) * batch;
+    int best = 0;
+    int64_t best_cost = 0;
+    for (int bn = 256; bn >= 64; bn /= 2) {
+        if (bn == 256 && N % 256 != 0) continue;
+        const int64_t tiles = mt * ceil_div(N, bn);
+        const int64_t cost = ceil_div64(tiles, kNumSMs) * (bn + 64);
+        if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best;
 }
 
 int split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, __half* out, cudaStream_t st, float scale) {

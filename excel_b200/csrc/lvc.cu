@@ -11,19 +11,44 @@
 
 namespace xl {
 
-// qt[b, m, c] = f[b, c, m] / max(||f[b, :, m]||, 1e-12): normalise over channels and transpose to [n_p, C]
-__global__ void lvc_normalize_t_kernel(const float* __restrict__ f, int C, int np, float* __restrict__ qt) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (m >= np) return;
-    const float* src = f + (int64_t)b * C * np + m;
+// qt[b, m, c] = f[b, c, m] / max(||f[b, :, m]||, 1e-12): normalise over channels and transpose to [n_p, C].
+// A block of 32 x 8 threads owns 32 positions: channel norms with coalesced reads along m (fixed summation order: channel
+// c in slice c % 8, slices combined 0..7), then 32 x 32 tiles transposed through shared memory so that the writes are
+// coalesced along c.
+__global__ void __launch_bounds__(256)
+lvc_normalize_t_kernel(const float* __restrict__ f, int C, int np, float* __restrict__ qt) {
+    __shared__ float part[8][33], tile[32][33], inv[32];
+    const int tx = threadIdx.x, ty = threadIdx.y, m0 = blockIdx.x * 32, b = blockIdx.y;
+    const float* src = f + (int64_t)b * C * np;
     float ss = 0.f;
-    for (int c = 0; c < C; ++c) {
-        const float v = src[(int64_t)c * np];
-        ss = fmaf(v, v, ss);
+    if (m0 + tx < np)
+        for (int c = ty; c < C; c += 8) {
+            const float v = src[(int64_t)c * np + m0 + tx];
+            ss = fmaf(v, v, ss);
+        }
+    part[ty][tx] = ss;
+    __syncthreads();
+    if (ty == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][tx];
+        inv[tx] = 1.f / fmaxf(sqrtf(t), 1e-12f);
     }
-    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    float* dst = qt + ((int64_t)b * np + m) * C;
-    for (int c = 0; c < C; ++c) dst[c] = src[(int64_t)c * np] * inv;
+    __syncthreads();
+    for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + ty + 8 * k;
+            tile[ty + 8 * k][tx] = (c < C && m0 + tx < np) ? src[(int64_t)c * np + m0 + tx] * inv[tx] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int m = m0 + ty + 8 * k;
+            if (m < np && c0 + tx < C) qt[((int64_t)b * np + m) * C + c0 + tx] = tile[tx][ty + 8 * k];
+        }
+        __syncthreads();
+    }
 }
 
 // rowsum[r] = sum_j x[r, j] in double, one warp per row
@@ -104,7 +129,7 @@ __global__ void centred_sigmoid_kernel(float* __restrict__ x, int64_t n, const f
 // normalise + similarity + batch mean, shared by the LVC bias and attn_pred: sim [B,np,np] and mean_ws[0]
 static int cosine_similarity_and_mean(const float* feats, int B, int C, int np, float* qt_ws, double* rowsum_ws, float* mean_ws,
                                       float* sim, cudaStream_t st) {
-    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 128), B), 128, 0, st>>>(feats, C, np, qt_ws);
+    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 32), B), dim3(32, 8), 0, st>>>(feats, C, np, qt_ws);
     if (int e = check_launch("lvc_normalize_t_kernel")) return e;
     // sim[b] = qt[b] qt[b]^T  (exact fp32)
     if (int e = sgemm2(qt_ws, qt_ws, sim, nullptr, nullptr, np, np, C, C, C, np, B, (int64_t)np * C, (int64_t)np * C,
