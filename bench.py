@@ -438,12 +438,14 @@ def run_cfg3(args):
     job = Job()
     dev, rank, world = job.dev, job.rank, job.world
     G, S, K, T = 64, 448, 80, 103
-    per = G // world
+    from excel_b200.evaluate import shard_slice
+    mine = shard_slice(G, rank, world)          # rank r owns a contiguous 64/W slice of each global batch
+    per = mine.stop - mine.start
     hp = ExCELHotPath(SurgeryViT(synth.random_visual_weights(seed=0), device=dev), synth.text_bank(T, 512, seed=1), K)
     host = []
-    for i in range(3):   # rank r owns a contiguous 64/W slice of each global batch
-        im = synth.images(G, S, seed=20 + i)[rank * per:(rank + 1) * per].contiguous().pin_memory()
-        cl = synth.class_labels(G, K, seed=120 + i, n_fixed=None, dataset="ms_coco")[rank * per:(rank + 1) * per].contiguous()
+    for i in range(3):
+        im = synth.images(G, S, seed=20 + i)[mine].contiguous().pin_memory()
+        cl = synth.class_labels(G, K, seed=120 + i, n_fixed=None, dataset="ms_coco")[mine].contiguous()
         host.append((im, cl))
     devb = [(i.to(dev), c) for i, c in host]
     ms, launches, clocks, _ = job.timed(lambda i: hp(devb[i % 3][0], devb[i % 3][1]), args.steps, args.warmup, sample_clocks=(rank == 0))

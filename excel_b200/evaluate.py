@@ -37,6 +37,14 @@ def scores_from_hist(hist):
     return {"pAcc": float(acc), "miou": float(np.nanmean(iu[valid])) if valid.any() else float("nan")}
 
 
+def shard_slice(global_batch, rank, world):
+    """Contiguous slice of a global batch owned by `rank` (cfg3's 64 images over 8 ranks -> 8 x 8); the first
+    `global_batch % world` ranks take one extra image."""
+    per, extra = divmod(global_batch, world)
+    lo = rank * per + min(rank, extra)
+    return slice(lo, lo + per + (1 if rank < extra else 0))
+
+
 def shard_indices(n, rank, world):
     """tools/infer_lam.py:166: rank r takes images r, r+W, r+2W, ..."""
     return list(range(rank, n, world))
