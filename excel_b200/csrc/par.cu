@@ -85,14 +85,20 @@ __device__ __forceinline__ void stage_tile_async(float* sm, const float* __restr
 //           differences to the centre pixel -- small where the image is smooth, so the one-pass
 //           sum / sum-of-squares form is well conditioned;
 //   pass 2: a_k = -mean_c[(|I_k - I_0| / (std_c + 1e-8) / w1)^2] kept in registers, softmax over k,
-//           + w2 * (constant positional softmax), streamed out with evict-first stores.
+//           + w2 * (constant positional softmax), streamed out.
 // STD: the reference's dilation set (1, 2, 4, 8, 12, 24; scripts/train_voc.py:112, tools/infer_lam.py:168) is baked in, so
 // that every neighbour address is an immediate offset of one base register -- the generic form spends a quarter of its
 // issue slots on address arithmetic (ncu: the kernel is issue-bound, not LDS- or HBM-bound).
 __device__ constexpr int kStdDil[6] = {1, 2, 4, 8, 12, 24};
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int NDIL, bool STD>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, float* __restrict__ aff,
                     int H, int W, int Wp, int halo_rt, ParGeom g, float w1, const int* __restrict__ img_index) {
     constexpr int K = 8 * NDIL;
@@ -137,15 +143,22 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
         }
         const float s0 = S0.x + S0.y, s1 = S1.x + S1.y, s2 = S2.x + S2.y;
         const float q0 = Q0.x + Q0.y, q1 = Q1.x + Q1.y, q2 = Q2.x + Q2.y;
-        const float r0 = invw / (sqrtf(fmaxf((q0 - s0 * s0 * invk) * invk1, 0.f)) + 1e-8f);
-        const float r1 = invw / (sqrtf(fmaxf((q1 - s1 * s1 * invk) * invk1, 0.f)) + 1e-8f);
-        const float r2 = invw / (sqrtf(fmaxf((q2 - s2 * s2 * invk) * invk1, 0.f)) + 1e-8f);
+        const float r0 = __fdividef(invw, sqrtf(fmaxf((q0 - s0 * s0 * invk) * invk1, 0.f)) + 1e-8f);
+        const float r1 = __fdividef(invw, sqrtf(fmaxf((q1 - s1 * s1 * invk) * invk1, 0.f)) + 1e-8f);
+        const float r2 = __fdividef(invw, sqrtf(fmaxf((q2 - s2 * s2 * invk) * invk1, 0.f)) + 1e-8f);
+        // Pass 2 RE-READS the neighbours (the barrier stops the compiler from carrying the 144 differences of pass 1 across: it
+        // did, at 128 registers and 2 CTAs per SM, with 212 B of spills).  Without the carry the kernel fits 85 registers: three
+        // CTAs (24 warps) per SM -- the kernel is latency-bound (ncu: 6 stall cycles per issue at 4 warps per scheduler), not
+        // pipe-bound, so the 50 % more warps are worth the 144 extra LDS per pixel.
+        asm volatile("" ::: "memory");
         float a[K];
         float amax = -INFINITY;
-        const float2 R0 = make_float2(r0, r0), R1 = make_float2(r1, r1), R2 = make_float2(r2, r2);
-        // -mean_c(t^2) * log2(e) (exp2 below); the channel mean as a multiplication: a true division costs a
-        // ~10-instruction slow-path check 48 times per pixel for at most 1 ulp of the exponent
-        const float2 KK = make_float2(-1.4426950408889634f / 3.f, -1.4426950408889634f / 3.f);
+        // a_k = -mean_c(t_c^2) * log2(e) (exp2 below) = sum_c d_c * (d_c * w_c), w_c = -(r_c^2) * log2(e) / 3: the channel mean, the
+        // 1/w1 and the 1/(std + eps) factors fold into one scalar per channel (a true division costs a ~10-instruction slow-path
+        // check 48 times per pixel for at most 1 ulp of the exponent)
+        constexpr float kk = -1.4426950408889634f / 3.f;
+        const float w0 = r0 * r0 * kk, w1c = r1 * r1 * kk, w2c = r2 * r2 * kk;
+        const float2 W0 = make_float2(w0, w0), W1 = make_float2(w1c, w1c), W2 = make_float2(w2c, w2c);
 #pragma unroll
         for (int di = 0; di < NDIL; ++di) {
             const int d = STD ? kStdDil[di] : g.dil[di], dW = d * TW;
@@ -153,25 +166,41 @@ par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64
             for (int t = 0; t < 8; t += 2) {
                 const float* pa = ctr + tap_dy(t) * dW + tap_dx(t) * d;
                 const float* pb = ctr + tap_dy(t + 1) * dW + tap_dx(t + 1) * d;
-                const float2 T0 = __fmul2_rn(__fadd2_rn(make_float2(pa[0], pb[0]), make_float2(-c0, -c0)), R0);
-                const float2 T1 = __fmul2_rn(__fadd2_rn(make_float2(pa[cs], pb[cs]), make_float2(-c1, -c1)), R1);
-                const float2 T2 = __fmul2_rn(__fadd2_rn(make_float2(pa[2 * cs], pb[2 * cs]), make_float2(-c2, -c2)), R2);
-                const float2 V = __fmul2_rn(__ffma2_rn(T2, T2, __ffma2_rn(T1, T1, __fmul2_rn(T0, T0))), KK);
+                const float2 D0 = __fadd2_rn(make_float2(pa[0], pb[0]), make_float2(-c0, -c0));
+                const float2 D1 = __fadd2_rn(make_float2(pa[cs], pb[cs]), make_float2(-c1, -c1));
+                const float2 D2 = __fadd2_rn(make_float2(pa[2 * cs], pb[2 * cs]), make_float2(-c2, -c2));
+                const float2 V = __ffma2_rn(__fmul2_rn(D2, W2), D2, __ffma2_rn(__fmul2_rn(D1, W1), D1, __fmul2_rn(__fmul2_rn(D0, W0), D0)));
                 a[di * 8 + t] = V.x;
                 a[di * 8 + t + 1] = V.y;
                 amax = fmaxf(amax, fmaxf(V.x, V.y));
             }
         }
-        float sum = 0.f;
+        // softmax over k in the exp2 domain: a_k - amax <= 0, so the bare MUFU (ex2.approx.ftz: results below 2^-126 flush to 0
+        // against a largest term of exactly 1) replaces exp2f's denormal-range scaling (an FSETP and two predicated FMULs
+        // per neighbour); subtraction, sum and the final a * inv + pos run on packed fp32x2 instructions.
+        const float2 NM = make_float2(-amax, -amax);
+        float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            a[k] = exp2f(a[k] - amax);
-            sum += a[k];
+        for (int k = 0; k < K; k += 2) {
+            const float2 x = __fadd2_rn(make_float2(a[k], a[k + 1]), NM);
+            a[k] = ex2_approx(x.x);
+            a[k + 1] = ex2_approx(x.y);
+            sum2 = __fadd2_rn(sum2, make_float2(a[k], a[k + 1]));
         }
-        const float inv = 1.f / sum;
+        const float inv = __fdividef(1.f, sum2.x + sum2.y);   // sum in [1, K]: MUFU.RCP, no slow-path call
+        const float2 INV = make_float2(inv, inv);
+        // one 64-bit pointer bumped by the plane stride per store (k * plane as an index costs ~8 integer instructions per store:
+        // a quarter of the kernel's instructions before this form)
         float* out = aff + ((int64_t)b * K * H + y) * Wp + x;
 #pragma unroll
-        for (int k = 0; k < K; ++k) out[k * plane] = fmaf(a[k], inv, g.pos[k]);
+        for (int k = 0; k < K; k += 2) {
+            const float2 v = __ffma2_rn(make_float2(a[k], a[k + 1]), INV, make_float2(g.pos[k], g.pos[k + 1]));
+            // (asm: the compiler otherwise rewrites the bump as base + k * plane)
+            asm volatile("st.global.f32 [%0], %1;" :: "l"(out), "f"(v.x) : "memory");
+            out += plane;
+            asm volatile("st.global.f32 [%0], %1;" :: "l"(out), "f"(v.y) : "memory");
+            out += plane;
+        }
     }
 }
 
@@ -497,6 +526,8 @@ template <typename Kern>
 static int set_smem(Kern kern, size_t bytes, const char* what) {
     XL_REQUIRE(bytes <= 227 * 1024, "%s: %zu B of shared memory (dilation too large for the tile)", what, bytes);
     XL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // whole 228 KB carve-out: three affinity CTAs of 75 KB (+1 KB reserved each) fill it exactly
+    XL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 
