@@ -217,19 +217,19 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 Sub qs = {0, 0, 0}, qp = {0, 0, 0};
                 int us = 0;
                 for (int up = 0; up < U; ++up) {
-                    for (; us < U && us < up + 4; ++us, ++gs) {   // ---- S(us) = X Y[64-key half]^T
-                        const int nsub = qs.kb < nblk - 1 ? 2 : nsub_last;
+                    // ---- S of one LOAD STEP (both 64-key halves: sub-steps us, us + 1) as ONE N = 128 instruction per k-step into the
+                    // adjacent buffer pair (gs, gs + 1): an M128 x N64 x K16 MMA re-reads the 4 KB X slice for 2 KB of Y and is bound by
+                    // the shared-memory operand bandwidth (65-80 clk against 32 of math); at N = 128 the X slice is read once per 4 KB of Y.
+                    for (; us < U && us + 1 < up + 4; us += 2, gs += 2) {
                         const uint32_t s = ls % kXYStages;
-                        if (qs.half == 0) {
-                            XL_TRACE(1);
-                            mbar_wait(&xy_full[s], (ls / kXYStages) & 1);
-                            tc_fence_after();
-                            XL_TRACE(2);
-                        }
-                        const int nvalid = min(64, p.N - qs.kb * 128 - qs.half * 64);   // may be <= 0: a 16-wide dummy tile
-                        const uint32_t idesc = make_idesc(nvalid > 0 ? (nvalid + 15) & ~15 : 16);
-                        const uint32_t tacc = tmem_base + (gs & 3) * 64;
-                        const uint32_t st = xy0 + s * kXYStage, yb = st + 2 * kTile + (uint32_t)qs.half * 8192u;   // Y rows 64..127: +64 x 128 B
+                        XL_TRACE(1);
+                        mbar_wait(&xy_full[s], (ls / kXYStages) & 1);
+                        tc_fence_after();
+                        XL_TRACE(2);
+                        const int nvalid = min(128, p.N - qs.kb * 128);              // >= 1; padding keys are not computed
+                        const uint32_t idesc = make_idesc((nvalid + 15) & ~15);
+                        const uint32_t tacc = tmem_base + (gs & 3) * 64;             // gs even: buffers (0, 1) or (2, 3)
+                        const uint32_t st = xy0 + s * kXYStage, yb = st + 2 * kTile;
                         const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTile);
                         const uint64_t b_hi = umma_desc_sw128(yb), b_lo = umma_desc_sw128(yb + kTile);
                         if (leader) {
@@ -241,11 +241,13 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                 umma_f16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, 1);
                             }
                             }
-                            if (qs.half == nsub - 1) umma_commit(&xy_empty[s]);
+                            umma_commit(&xy_empty[s]);
                             umma_commit(&s_full[gs & 3]);
+                            umma_commit(&s_full[(gs + 1) & 3]);
                         }
                         XL_TRACE(3);
-                        if (qs.half == nsub - 1) ++ls;
+                        ++ls;
+                        next(qs);
                         next(qs);
                     }
                     // ---- PV(up): O_hh += P[64 keys] V_hh
@@ -313,6 +315,29 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const int hc = min(hpi, p.H - g * hpi);
                 const int zo = p.gsplit ? g * p.B + b : b;            // map slice of this item
                 const float* mrow = p.ml + ((int64_t)b * p.H + g * hpi) * p.N + row;   // + hh * N
+                // The head-reduced map block of a key block (this warp: 32 rows x 32 keys) leaves as two 16-column chunks through the
+                // warp's single staging block.  Chunk 0 goes out right after the key block's last head; chunk 1 is DEFERRED until
+                // after the first head step of the next key block: by then the bulk engine (whose queue is full of operand loads) has
+                // long read chunk 0 out of the staging block, where a back-to-back second chunk waited ~3000 clocks for it.
+                float pend[16];
+                int pend_kc = -1;                                     // key column of the deferred chunk (-1: none)
+                const float cf = p.coef * (1.f / 1024.f);
+                auto flush_chunk = [&](const float (&v)[16], int kc) {
+                    if (lane == 0) tma_store_wait_read<0>();          // the previous chunk has left the staging buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                            make_float4(cf * v[4 * j], cf * v[4 * j + 1], cf * v[4 * j + 2], cf * v[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        // a plain store for the first head group, a reduce-add (performed in L2) for the others
+                        if (g == 0 || p.gsplit) tma_store_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
+                        else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
+                        tma_store_commit();
+                    }
+                };
                 for (int kb = 0; kb < nblk; ++kb) {
                     const int key0 = kb * 128 + grp * 64 + cq * 32;   // this warp's 32 keys of the key block
                     float acc[2][16];
@@ -329,6 +354,11 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         mbar_wait(&s_full[buf], (u >> 2) & 1);
                         tc_fence_after();
                         XL_TRACE(9);
+                        if (nrow <= 0) {   // (warp-uniform) none of this warp's rows exists: their P (and O) rows are never read back
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&p_ready[buf]);
+                            continue;
+                        }
                         // Only the LAST key block of an image can hold padding keys.  The two cases are separate instantiations of the
                         // chunk code: written as one body, the per-element `key >= N ? -inf : s` test was if-converted and ran
                         // (ISETP + SEL per element, a quarter of the epilogue's instructions) for every key block.
@@ -402,34 +432,27 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&p_ready[buf]);
                         XL_TRACE(11);
+                        if (hh == 0 && pend_kc >= 0) {               // the previous key block's second chunk
+                            flush_chunk(pend, pend_kc);
+                            pend_kc = -1;
+                        }
                     }
-                    // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads, 16 columns at a time through
-                    // the warp's private staging block (SWIZZLE_64B rows) and out by TMA: a plain store for the first head group,
-                    // a reduce-add (performed in L2) for the others -- no thread waits on global memory.
+                    // head-reduced map of this key block: coef * 2^-10 * sum over the group's heads -- no thread waits on global memory
                     XL_TRACE(12);
-                    if (nrow > 0 && !XL_PV(32)) {
-                        const float cf = p.coef * (1.f / 1024.f);
+                    if (nrow > 0 && !XL_PV(32) && key0 < p.N) {
+                        flush_chunk(acc[0], key0);
+                        XL_TRACE(13);
+                        if (key0 + 16 < p.N) {
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int kc = key0 + c * 16;
-                            if (kc >= p.N) break;   // (uniform)
-                            if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
-                            __syncwarp();
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                *reinterpret_cast<float4*>(stg + lane * 16 + ((j ^ ((lane >> 1) & 3)) << 2)) =
-                                    make_float4(cf * acc[c][4 * j], cf * acc[c][4 * j + 1], cf * acc[c][4 * j + 2], cf * acc[c][4 * j + 3]);
-                            fence_proxy_async_smem();
-                            __syncwarp();
-                            if (lane == 0) {
-                                if (g == 0 || p.gsplit) tma_store_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
-                                else tma_reduce_add_3d(&tmO, stg, kc, rb * 128 + lg * 32, zo);
-                                tma_store_commit();
-                            }
-                            XL_TRACE(13);
+                            for (int e = 0; e < 16; ++e) pend[e] = acc[1][e];
+                            pend_kc = key0 + 16;
                         }
                     }
                     XL_TRACE(14);
+                }
+                if (pend_kc >= 0) {                                   // last key block of the group
+                    flush_chunk(pend, pend_kc);
+                    pend_kc = -1;
                 }
                 if (lane == 0) tma_store_wait_all<0>();   // this group's map blocks are performed before the next group adds to them
                 // ---- O of head hh = qt of the group: TMEM -> split fp16 -> o[b*N + row, h*64 ..] (hi) / [.. + D] (lo)

@@ -183,6 +183,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             decode(item, 0, b, h, rb, kb);
             const int row = rb * 128 + trow;
             const bool row_ok = row < p.N;
+            const bool rows_empty = rb * 128 + lg * 32 >= p.N;    // this warp's 32 rows lie past the image: no TMEM reads, no exp stream
             float m_run = -INFINITY, l_run = 0.f;                 // MODE 0
             float acc[32];                                        // MODE 1: head-summed probabilities
             if (MODE == 1) {
@@ -209,6 +210,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     if ((it & 1) != grp) continue;
                     mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
                     tc_fence_after();
+                    if (rows_empty) {   // (warp-uniform) none of this warp's 32 rows exists (N = 128 q + 1: the last row block holds one row)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                        continue;
+                    }
                     // Only the LAST key block can hold padding keys: the chunk code is instantiated twice so that the per-element
                     // `key >= N ? -inf : s` selection (if-converted by the compiler) does not run for the other key blocks.
                     auto chunks = [&](auto tail_tag) {
@@ -263,6 +269,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 mbar_wait(&acc_full[buf], (it / kAAcc) & 1);
                 tc_fence_after();
+                if (rows_empty) {       // (warp-uniform) see MODE 0
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    continue;
+                }
                 const int key0 = kb * 128 + qt * 32;
                 auto tile = [&](auto tail_tag) {   // (two instantiations: see MODE 0)
                 constexpr bool TAIL = decltype(tail_tag)::value;
