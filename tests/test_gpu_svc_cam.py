@@ -117,6 +117,36 @@ def test_refine_batch_vs_oracle():
         assert hard == 0 and total <= 4, (b, hard, total)
 
 
+@pytest.mark.parametrize("out_hw", [(75, 91), (120, 166), (53, 40)])
+def test_dropin_refine_at_label_resolution_vs_oracle(out_hw):
+    """tools/infer_lam.py:93-94: the per-image calls with PAR at the LABEL resolution (the original image size: any H x W,
+    rows that are not 16 B multiples, larger or smaller than the network input) -- the image goes through the
+    align_corners=True resize of utils/PAR.py:67, the CAMs through cv2-style bilinear up-sampling (utils/affutils.py:75)."""
+    from excel_b200 import affutils
+    from excel_b200.par import PAR
+    S, K = 96, 20
+    g = S // 16
+    N = g * g + 1
+    gen = torch.Generator().manual_seed(out_hw[0])
+    attn = torch.rand(8, N, N, generator=gen) + 0.01
+    attr = torch.nn.functional.interpolate(torch.rand(1, K, 3, 3, generator=gen), size=(g, g), mode="bicubic")[0]
+    attr = (attr - attr.amin((1, 2), keepdim=True)) / (attr.amax((1, 2), keepdim=True) - attr.amin((1, 2), keepdim=True))
+    attr = attr.reshape(K, g * g).t().contiguous()
+    cls = torch.zeros(K)
+    cls[[2, 7, 11]] = 1
+    img = synth.images(1, S, seed=out_hw[1])[0]
+    par = PAR(port.PAR_DILATIONS, 20)
+    refined, cls_lst = affutils.refine_cams_with_aff(attr.cuda(), attn.cuda(), cls.cuda(), (S, S), caa_thre=0.79)
+    labels, planes = affutils.refine_cams_with_bkg_weclip(refined, img.cuda(), cls_lst, par, out_hw)
+    lst, cl = port.refine_cams_with_aff(attr, attn, cls, (S, S), caa_thre=0.79)
+    lab, cams, ref_planes = port.refine_cams_with_bkg_weclip(lst, img, cl, out_hw)
+    assert labels.shape == (1,) + tuple(out_hw) and torch.equal(cls_lst, cl)
+    err = (planes.cpu() - cams).abs().max().item()
+    assert err < 2e-4, err
+    hard, total = label_parity(ref_planes, lab[0], labels[0].cpu(), plane_err=err)
+    assert hard == 0 and total <= 8, (hard, total, err)
+
+
 def test_label_utils_golden(golden):
     """utils/camutils.py:123-143,438-476 on the device vs the reference fixtures (integer outputs: bit-exact)."""
     from excel_b200 import camutils
