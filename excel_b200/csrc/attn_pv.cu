@@ -93,6 +93,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* o_empty = o_full + 1;           // O drained (epilogue -> MMA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.N + 127) / 128;
     const int hpi = p.hpi;                                  // heads per group (1, 2 or 4)
@@ -117,6 +118,7 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 256;
+    pdl_wait();
     constexpr uint32_t kIdescPV = make_idesc_bmn(64);   // B = V [keys, head dim]: MN-major
 
     // A "load step" is one (key block kb, head hh) pair: one X / Y stage and one V^T stage.  It is consumed as one or two
@@ -500,6 +502,8 @@ attn_pv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // out[i] = sum_g part[g][i] in the fixed order g = 0, 1, ... (split launches: one partial head-sum map per head group)
 __global__ void __launch_bounds__(256)
 attn_combine_kernel(const float4* __restrict__ part, int ngrp, int64_t slice4, float4* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < slice4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 a = __ldcs(part + i);
         for (int g = 1; g < ngrp; ++g) {
@@ -523,13 +527,13 @@ int attn_pv(const CUtensorMap& tmQ, const AttnPvParams& p, cudaStream_t st) {
     CUtensorMap tmO;
     if (int e = make_map_store(&tmO, p.gsplit ? p.part : p.out, p.gsplit ? p.B * ngrp : p.B, p.N)) return e;
     const int items = p.B * nblk * (p.gsplit ? ngrp : 1);
-    attn_pv_kernel<<<items < kNumSMs ? items : kNumSMs, kPvThreads, kPvSmem, st>>>(tmQ, tmO, p);
+    XL_CUDA(launch_pdl(attn_pv_kernel, dim3(items < kNumSMs ? items : kNumSMs), dim3(kPvThreads), kPvSmem, st, tmQ, tmO, p));
     if (int e = check_launch("attn_pv_kernel")) return e;
     if (!p.gsplit) return 0;
     const int64_t slice4 = (int64_t)p.B * p.N * Npad / 4;
     const int64_t blocks = ceil_div64(slice4, 256 * 2);
-    attn_combine_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(
-        reinterpret_cast<const float4*>(p.part), ngrp, slice4, reinterpret_cast<float4*>(p.out));
+    XL_CUDA(launch_pdl(attn_combine_kernel, dim3((unsigned)(blocks < 148 * 8 ? blocks : 148 * 8)), dim3(256), 0, st,
+                       reinterpret_cast<const float4*>(p.part), ngrp, slice4, reinterpret_cast<float4*>(p.out)));
     return check_launch("attn_combine_kernel");
 }
 

@@ -61,6 +61,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint8_t* yring = tiles + 2 * 2 * kATile;
     constexpr int NST = MODE == 0 ? kAYStages : kAStages;
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = (p.N + 127) / 128;                   // row blocks == key blocks
     const int TH = p.ntypes * p.H;                        // (score set, head) pairs
@@ -87,6 +88,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     // work item -> (b, th, rb, kb); th = type * H + head; j = position inside the item
     auto decode = [&](int item, int j, int& b, int& h, int& rb, int& kb) {
@@ -393,7 +395,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, cudaStream_t st, bo
     XL_REQUIRE(p.m && (p.out || p.out_split || stats_only), "attn_scores: missing buffers");
     const int nblk = (p.N + 127) / 128;
     const int items0 = p.B * p.ntypes * p.H * nblk, items1 = p.B * nblk * nblk;
-    attn_tc_kernel<0><<<items0 < kNumSMs ? items0 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmQ, p);
+    XL_CUDA(launch_pdl(attn_tc_kernel<0>, dim3(items0 < kNumSMs ? items0 : kNumSMs), dim3(kAThreads), kASmem, st, tmQ, tmQ, p));
     if (int e = check_launch("attn_tc_kernel<stats>")) return e;
     if (stats_only) return 0;
     CUtensorMap tmO;
@@ -405,7 +407,7 @@ int attn_scores(const CUtensorMap& tmQ, const AttnParams& p, cudaStream_t st, bo
         const uint32_t box[3] = {16, 32, 1};
         if (int e = encode_tensor_map(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, p.out_split, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return e;
     } else if (int e = make_map_store(&tmO, p.out, p.B, p.N)) return e;
-    attn_tc_kernel<1><<<items1 < kNumSMs ? items1 : kNumSMs, kAThreads, kASmem, st>>>(tmQ, tmO, p);
+    XL_CUDA(launch_pdl(attn_tc_kernel<1>, dim3(items1 < kNumSMs ? items1 : kNumSMs), dim3(kAThreads), kASmem, st, tmQ, tmO, p));
     return check_launch("attn_tc_kernel<map>");
 }
 

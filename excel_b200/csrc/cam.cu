@@ -21,6 +21,8 @@ namespace xl {
 // ---- image_features / image_features.norm(dim=1)  (norm over the TOKEN axis, clip/clip.py:353) -------
 __global__ void __launch_bounds__(1024)
 token_sumsq_kernel(const float* __restrict__ tok, int N, int E, float* __restrict__ norm) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32][33];
     const int e = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
     float s = 0.f;
@@ -41,6 +43,8 @@ token_sumsq_kernel(const float* __restrict__ tok, int N, int E, float* __restric
 
 __global__ void token_div_kernel(const float* __restrict__ tok, const float* __restrict__ norm, float* __restrict__ out,
                                  int N, int E, int64_t total) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int e = (int)(i % E);
@@ -51,6 +55,8 @@ __global__ void token_div_kernel(const float* __restrict__ tok, const float* __r
 // ---- operand pre-scale: amax -> power of two (device side, no host sync) --------------------------------
 __global__ void __launch_bounds__(256)
 amax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ amax) {
+    pdl_trigger();
+    pdl_wait();
     float m = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
     m = warp_max(m);
@@ -63,6 +69,8 @@ __device__ __forceinline__ float pow2_scale(float amax) {
 }
 __global__ void __launch_bounds__(256)
 split_scaled_kernel(const float* __restrict__ x, int64_t ldx, int cols, int Kp, __half* __restrict__ out, const float* __restrict__ amax) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t r = blockIdx.y;
     if (c >= Kp) return;
@@ -77,6 +85,8 @@ constexpr int kCamRows = 64, kCamSlots = 16;   // T <= 32 * kCamSlots
 __global__ void __launch_bounds__(256)
 cam_sim_kernel(const float* __restrict__ S, int Tp, const float* __restrict__ amax2, float* __restrict__ sim, float* __restrict__ part,
                int N, int T, int nblk) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sh[];            // w[T], then [8][T] min, [8][T] max
     __shared__ float red[32];
     float* w = sh;
@@ -142,6 +152,8 @@ cam_sim_kernel(const float* __restrict__ S, int Tp, const float* __restrict__ am
 // ---- (sim - min_n) / (max_n - min_n) per (b,t), in place; min / max over ALL N tokens from the block partials ----
 __global__ void __launch_bounds__(256)
 cam_norm_kernel(float* __restrict__ sim, const float* __restrict__ part, int N, int T, int nblk) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sh[];            // lo[T], rng[T]
     const int b = blockIdx.y;
     for (int t = threadIdx.x; t < T; t += 256) {
@@ -171,10 +183,10 @@ extern "C" int excel_token_normalize(const float* tok, int B, int N, int E, floa
     XL_REQUIRE(B >= 0 && N >= 1 && E >= 1 && B <= 65535, "token_normalize: bad shape");
     if (B == 0) return 0;
     dim3 grid(ceil_div(E, 32), B), block(32, 32);
-    token_sumsq_kernel<<<grid, block, 0, st>>>(tok, N, E, norm_ws);
+    XL_CUDA(launch_pdl(token_sumsq_kernel, dim3(grid), dim3(block), 0, st, tok, N, E, norm_ws));
     if (int e = check_launch("token_sumsq_kernel")) return e;
     const int64_t total = (int64_t)B * N * E;
-    token_div_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(tok, norm_ws, out, N, E, total);
+    XL_CUDA(launch_pdl(token_div_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, st, tok, norm_ws, out, N, E, total));
     return check_launch("token_div_kernel");
 }
 
@@ -236,16 +248,16 @@ extern "C" int excel_cam_surgery(const float* feats, const float* text, int B, i
     float* S = (float*)take(M * Tp * 4);
     float* part = (float*)take((int64_t)B * nblk * 2 * T * 4);
     XL_CUDA(cudaMemsetAsync(amax, 0, 16, st));
-    amax_kernel<<<(unsigned)(ceil_div64(M * E, 256 * 8) < 4 * kNumSMs ? ceil_div64(M * E, 256 * 8) : 4 * kNumSMs), 256, 0, st>>>(feats, M * E, amax);
+    XL_CUDA(launch_pdl(amax_kernel, dim3((unsigned)(ceil_div64(M * E, 256 * 8) < 4 * kNumSMs ? ceil_div64(M * E, 256 * 8) : 4 * kNumSMs)), dim3(256), 0, st, feats, M * E, amax));
     if (int e = check_launch("amax_kernel")) return e;
-    amax_kernel<<<(unsigned)(ceil_div64((int64_t)T * E, 256) < kNumSMs ? ceil_div64((int64_t)T * E, 256) : kNumSMs), 256, 0, st>>>(text, (int64_t)T * E, amax + 1);
+    XL_CUDA(launch_pdl(amax_kernel, dim3((unsigned)(ceil_div64((int64_t)T * E, 256) < kNumSMs ? ceil_div64((int64_t)T * E, 256) : kNumSMs)), dim3(256), 0, st, text, (int64_t)T * E, amax + 1));
     if (int e = check_launch("amax_kernel")) return e;
     for (int64_t r0 = 0; r0 < M; r0 += 65535) {
         const int nr = (int)(M - r0 < 65535 ? M - r0 : 65535);
-        split_scaled_kernel<<<dim3(ceil_div(Ep, 256), nr), 256, 0, st>>>(feats + r0 * E, E, E, Ep, Fs + r0 * 2 * Ep, amax);
+        XL_CUDA(launch_pdl(split_scaled_kernel, dim3(dim3(ceil_div(Ep, 256), nr)), dim3(256), 0, st, feats + r0 * E, E, E, Ep, Fs + r0 * 2 * Ep, amax));
         if (int e = check_launch("split_scaled_kernel")) return e;
     }
-    split_scaled_kernel<<<dim3(ceil_div(Ep, 256), T), 256, 0, st>>>(text, E, E, Ep, Ts, amax + 1);
+    XL_CUDA(launch_pdl(split_scaled_kernel, dim3(dim3(ceil_div(Ep, 256), T)), dim3(256), 0, st, text, E, E, Ep, Ts, amax + 1));
     if (int e = check_launch("split_scaled_kernel")) return e;
     // S[B*N, T] (pitch Tp) = F_s T_s^T on the tensor cores: M128 x N64/128 tiles, K = Ep
     CUtensorMap tmA, tmB;
@@ -257,9 +269,9 @@ extern "C" int excel_cam_surgery(const float* feats, const float* text, int B, i
     q.C = S; q.ldc = Tp; q.alpha = 1.f;
     if (int e = tc_gemm(tmA, tmB, q, 1, bn, st)) return e;
     const size_t sm1 = (size_t)(17 * T) * sizeof(float), sm2 = (size_t)(2 * T) * sizeof(float);
-    cam_sim_kernel<<<dim3(nblk, B), 256, sm1, st>>>(S, Tp, amax, out, part, N, T, nblk);
+    XL_CUDA(launch_pdl(cam_sim_kernel, dim3(dim3(nblk, B)), dim3(256), sm1, st, S, Tp, amax, out, part, N, T, nblk));
     if (int e = check_launch("cam_sim_kernel")) return e;
     const int gx = (int)(ceil_div64((int64_t)N * T, 256 * 4) < 64 ? ceil_div64((int64_t)N * T, 256 * 4) : 64);
-    cam_norm_kernel<<<dim3(gx, B), 256, sm2, st>>>(out, part, N, T, nblk);
+    XL_CUDA(launch_pdl(cam_norm_kernel, dim3(dim3(gx, B)), dim3(256), sm2, st, out, part, N, T, nblk));
     return check_launch("cam_norm_kernel");
 }

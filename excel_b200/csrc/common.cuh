@@ -87,4 +87,28 @@ struct OpSum { __device__ float operator()(float a, float b) const { return a + 
 struct OpMax { __device__ float operator()(float a, float b) const { return fmaxf(a, b); } };
 struct OpMin { __device__ float operator()(float a, float b) const { return fminf(a, b); } };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// The encoder is a chain of ~190 short dependent kernels.  Launched with the programmatic-stream-serialization attribute, a
+// kernel's CTAs may become resident while the previous kernel's last CTAs are still running: launch latency, barrier init,
+// tensor-memory allocation and descriptor prefetch then overlap the predecessor's tail.  Every kernel launched this way calls
+// pdl_wait() before its first global-memory access (it returns once the preceding grid has completed and its writes are
+// visible) and pdl_trigger() at its top (lets ITS successor be scheduled early).  Both are no-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace xl

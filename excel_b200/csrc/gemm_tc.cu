@@ -65,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* acc_empty = acc_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr uint32_t kIdesc = make_idesc(kBN);
     constexpr uint32_t kTxBytes = 2 * kTileBytes + 2 * kBN * kBK * 2;
@@ -85,6 +86,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // the producers of A / B / residual have completed (set-up above overlapped their tail)
 
     auto decode = [&](int t, int& m0, int& n0, int& z1, int& z2) {
         const int nt = t % tiles_n, r = t / tiles_n;
@@ -453,7 +455,7 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
     }
     const bool res = tma_epi && p.C != nullptr && p.residual != nullptr;   // (the non-TMA fallback epilogue reads the residual itself)
 #define XL_TC_LAUNCH(BN_, EPI_, RES_) \
-    gemm_tc_kernel<BN_, EPI_, RES_><<<grid, kTcThreads, tc_smem(BN_), st>>>(tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total)
+    XL_CUDA(launch_pdl(gemm_tc_kernel<BN_, EPI_, RES_>, dim3(grid), dim3(kTcThreads), tc_smem(BN_), st, tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total))
 #define XL_TC_PICK(BN_) \
     do { if (!tma_epi) XL_TC_LAUNCH(BN_, false, false); else if (res) XL_TC_LAUNCH(BN_, true, true); else XL_TC_LAUNCH(BN_, true, false); } while (0)
     if (bn == 256) XL_TC_PICK(256);

@@ -27,6 +27,8 @@ struct ParGeom {
 // bilinear resize, align_corners=True (utils/PAR.py:67).  One thread per output pixel.
 __global__ void par_resize_ac_kernel(const float* __restrict__ src, int64_t sb, int64_t sc, int64_t sy,
                                      float* __restrict__ dst, int hi, int wi, int H, int W, const int* __restrict__ img_index) {
+    pdl_trigger();
+    pdl_wait();
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int bc = blockIdx.z;  // b*3 + c
@@ -116,6 +118,8 @@ template <int NDIL, bool STD>
 __global__ void __launch_bounds__(256, 3)
 par_affinity_kernel(const float* __restrict__ img, int64_t sb, int64_t sc, int64_t sy, float* __restrict__ aff,
                     int H, int W, int Wp, int halo_rt, ParGeom g, float w1, const int* __restrict__ img_index) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int K = 8 * NDIL;
     extern __shared__ float sm[];
     const int halo = STD ? 24 : halo_rt;
@@ -359,6 +363,8 @@ __global__ void __launch_bounds__(8 * TY + 32, 1)
 par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_constant__ CUtensorMap tm_in, int tma_in,
                    const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ plane_off, int img0,
                    int H, int W, int halo_rt, ParGeom g) {
+    pdl_trigger();
+    pdl_wait();
     const int halo = STD ? 24 : halo_rt;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST], tile_full, tile_empty;
@@ -484,6 +490,8 @@ par_iterate_kernel(const __grid_constant__ CUtensorMap tm_aff, const __grid_cons
 __global__ void par_labels_kernel(const float* __restrict__ planes, const int* __restrict__ plane_off,
                                   const int64_t* __restrict__ key, int64_t* __restrict__ labels, int64_t hw,
                                   const int* __restrict__ out_index) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (i >= hw) return;
@@ -562,12 +570,12 @@ static int launch_affinity(const float* img, int64_t sb, int64_t sc, int64_t sy,
     if constexpr (NDIL == 6) {
         if (is_std_dilations(g)) {
             if (int e = set_smem(par_affinity_kernel<6, true>, smem, "par_affinity")) return e;
-            par_affinity_kernel<6, true><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index);
+            XL_CUDA(launch_pdl(par_affinity_kernel<6, true>, dim3(grid), dim3(block), smem, st, img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index));
             return check_launch("par_affinity_kernel<std>");
         }
     }
     if (int e = set_smem(par_affinity_kernel<NDIL, false>, smem, "par_affinity")) return e;
-    par_affinity_kernel<NDIL, false><<<grid, block, smem, st>>>(img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index);
+    XL_CUDA(launch_pdl(par_affinity_kernel<NDIL, false>, dim3(grid), dim3(block), smem, st, img, sb, sc, sy, aff, H, W, Wp, halo, g, w1, img_index));
     return check_launch("par_affinity_kernel");
 }
 
@@ -589,13 +597,13 @@ static int launch_iterate_c(const CUtensorMap& tm, const CUtensorMap* tm_in, con
     dim3 grid(ceil_div(W, kTX), ceil_div(H, TY), nimg);
     if (is_std_dilations(g)) {
         if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG, true>, smem, "par_iterate")) return e;
-        par_iterate_kernel<CCH, TY, NST, KG, true><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in,
-                                                                                  out, plane_off, img0, H, W, halo, g);
+        XL_CUDA(launch_pdl(par_iterate_kernel<CCH, TY, NST, KG, true>, dim3(grid), dim3(8 * TY + 32), smem, st, tm, tm_in ? *tm_in : tm, tm_in != nullptr, in,
+                                                                                  out, plane_off, img0, H, W, halo, g));
         return check_launch("par_iterate_kernel<std>");
     }
     if (int e = set_smem(par_iterate_kernel<CCH, TY, NST, KG, false>, smem, "par_iterate")) return e;
-    par_iterate_kernel<CCH, TY, NST, KG, false><<<grid, 8 * TY + 32, smem, st>>>(tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
-                                                                             plane_off, img0, H, W, halo, g);
+    XL_CUDA(launch_pdl(par_iterate_kernel<CCH, TY, NST, KG, false>, dim3(grid), dim3(8 * TY + 32), smem, st, tm, tm_in ? *tm_in : tm, tm_in != nullptr, in, out,
+                                                                             plane_off, img0, H, W, halo, g));
     return check_launch("par_iterate_kernel");
 }
 
@@ -649,7 +657,7 @@ extern "C" int excel_par_forward(const float* img, int64_t stride_b, int64_t str
         XL_REQUIRE(resize_ws != nullptr, "PAR: image %dx%d != mask %dx%d needs a resize workspace", hi, wi, H, W);
         XL_REQUIRE(B * 3 <= 65535, "PAR: B too large for the resize launch");
         dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B * 3), block(32, 8);
-        par_resize_ac_kernel<<<grid, block, 0, st>>>(img, stride_b, stride_c, stride_y, resize_ws, hi, wi, H, W, img_index_dev);
+        XL_CUDA(launch_pdl(par_resize_ac_kernel, dim3(grid), dim3(block), 0, st, img, stride_b, stride_c, stride_y, resize_ws, hi, wi, H, W, img_index_dev));
         if (int e = check_launch("par_resize_ac_kernel")) return e;
         img = resize_ws;
         stride_y = W; stride_c = (int64_t)H * W; stride_b = 3 * stride_c;
@@ -713,6 +721,6 @@ extern "C" int excel_par_labels(const float* planes, const int* plane_off_dev, c
     XL_REQUIRE(B <= 65535, "PAR labels: B=%d > 65535", B);
     const int64_t hw = (int64_t)H * W;
     dim3 grid((unsigned)ceil_div64(hw, 256), B);
-    par_labels_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(planes, plane_off_dev, plane_key_dev, labels, hw, out_index_dev);
+    XL_CUDA(launch_pdl(par_labels_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, planes, plane_off_dev, plane_key_dev, labels, hw, out_index_dev));
     return check_launch("par_labels_kernel");
 }

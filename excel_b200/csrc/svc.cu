@@ -23,6 +23,8 @@ namespace xl {
 // attn: [L,B,N,N]; A: [B,n_p,n_p], n_p = N-1.  One thread per output element, x fastest.
 __global__ void svc_mean_kernel(const float* __restrict__ attn, int64_t stride_l, int64_t stride_b, int64_t stride_r, int N,
                                 int l0, int nl, float* __restrict__ A) {
+    pdl_trigger();
+    pdl_wait();
     const int np = N - 1;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y, b = blockIdx.z;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256)
 svc_rowpass_kernel(const float* __restrict__ A, const int* __restrict__ img_of, const float* __restrict__ x,
                    const float* __restrict__ si, const float* __restrict__ so, const float* __restrict__ add,
                    float* __restrict__ y, int np, int mode) {
+    pdl_trigger();
+    pdl_wait();
     const int q = blockIdx.y, b = img_of ? img_of[q] : q;
     const int lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= np) return;
@@ -104,6 +108,8 @@ __global__ void __launch_bounds__(1024)
 svc_colpass_kernel(const float* __restrict__ A, const int* __restrict__ img_of, const float* __restrict__ x,
                    const float* __restrict__ si, const float* __restrict__ so, const float* __restrict__ add,
                    float* __restrict__ y, int np, int mode) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32][33];
     const int q = blockIdx.y, b = img_of ? img_of[q] : q;
     const int cx = threadIdx.x, ry = threadIdx.y;
@@ -139,6 +145,8 @@ __global__ void __launch_bounds__(1024)
 svc_boxmask_kernel(const float* __restrict__ attr, int64_t attr_stride_b, int64_t attr_stride_p, const int* __restrict__ img_of,
                    const int* __restrict__ cls_of, int gh, int gw, double caa_thre, float* __restrict__ v,
                    float* __restrict__ mask_out) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ int sh[];
     const int n = gh * gw;
     int* label = sh;                 // [n] component label (min cell index) or -1
@@ -220,6 +228,8 @@ svc_boxmask_kernel(const float* __restrict__ attr, int64_t attr_stride_b, int64_
 // ---- per-class min-max, bilinear up-sampling, background channel (affutils.py:55-78,161-166) ----------
 __global__ void __launch_bounds__(256)
 svc_minmax_kernel(const float* __restrict__ x, int n, float* __restrict__ mn, float* __restrict__ mx) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[32];
     const float* p = x + (int64_t)blockIdx.x * n;
     float lo = INFINITY, hi = -INFINITY;
@@ -241,6 +251,8 @@ svc_minmax_kernel(const float* __restrict__ x, int n, float* __restrict__ mn, fl
 __global__ void __launch_bounds__(256)
 svc_upsample_bg_kernel(const float* __restrict__ refined, const float* __restrict__ mn, const float* __restrict__ rng,
                        const int* __restrict__ plane_off, int gh, int gw, int H, int W, float* __restrict__ planes) {
+    pdl_trigger();
+    pdl_wait();
     const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, b = blockIdx.z;
     if (x >= W || y >= H) return;
     const int p0 = plane_off[b], nc = plane_off[b + 1] - p0 - 1;  // plane p0 is the background
@@ -300,7 +312,7 @@ extern "C" int excel_svc_mean_attention(const float* attn, int64_t stride_l, int
     const int nl = attn_layers < L ? attn_layers : L, np = N - 1;
     XL_REQUIRE(np <= 65535 && B <= 65535, "svc_mean_attention: grid too large");
     dim3 grid(ceil_div(np, 256), np, B);
-    svc_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(attn, stride_l, stride_b, stride_r, N, L - nl, nl, A);
+    XL_CUDA(launch_pdl(svc_mean_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, attn, stride_l, stride_b, stride_r, N, L - nl, nl, A));
     return check_launch("svc_mean_kernel");
 }
 
@@ -321,13 +333,13 @@ extern "C" int excel_svc_seg_attention(const float* attn, int64_t stride_l, int6
 static int rowpass(const float* A, const int* img_of, const float* x, const float* si, const float* so, const float* add,
                    float* y, int Q, int np, int mode, cudaStream_t st) {
     dim3 grid(ceil_div(np, 8), Q);
-    svc_rowpass_kernel<<<grid, 256, 0, st>>>(A, img_of, x, si, so, add, y, np, mode);
+    XL_CUDA(launch_pdl(svc_rowpass_kernel, dim3(grid), dim3(256), 0, st, A, img_of, x, si, so, add, y, np, mode));
     return check_launch("svc_rowpass_kernel");
 }
 static int colpass(const float* A, const int* img_of, const float* x, const float* si, const float* so, const float* add,
                    float* y, int Q, int np, int mode, cudaStream_t st) {
     dim3 grid(ceil_div(np, 32), Q), block(32, 32);
-    svc_colpass_kernel<<<grid, block, 0, st>>>(A, img_of, x, si, so, add, y, np, mode);
+    XL_CUDA(launch_pdl(svc_colpass_kernel, dim3(grid), dim3(block), 0, st, A, img_of, x, si, so, add, y, np, mode));
     return check_launch("svc_colpass_kernel");
 }
 
@@ -352,8 +364,8 @@ extern "C" int excel_svc_box_mask(const float* attr, int64_t attr_stride_b, int6
     XL_REQUIRE(smem <= 200 * 1024, "svc_box_mask: grid %dx%d too large for the shared-memory labelling", gh, gw);
     XL_CUDA(cudaFuncSetAttribute(svc_boxmask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = n >= 1024 ? 1024 : ((n + 31) / 32) * 32;
-    svc_boxmask_kernel<<<Q, threads, smem, (cudaStream_t)stream>>>(attr, attr_stride_b, attr_stride_p, img_of_dev,
-                                                                   cls_of_dev, gh, gw, caa_thre, v, mask_out);
+    XL_CUDA(launch_pdl(svc_boxmask_kernel, dim3(Q), dim3(threads), smem, (cudaStream_t)stream, attr, attr_stride_b, attr_stride_p, img_of_dev,
+                                                                   cls_of_dev, gh, gw, caa_thre, v, mask_out));
     return check_launch("svc_boxmask_kernel");
 }
 
@@ -382,10 +394,10 @@ extern "C" int excel_svc_cams_to_planes(const float* refined, int Q, int gh, int
     XL_REQUIRE(Q >= 0 && B >= 0 && gh >= 1 && gw >= 1 && H >= 1 && W >= 1 && B <= 65535, "svc_cams_to_planes: bad shape");
     if (B == 0) return 0;
     if (Q > 0) {
-        svc_minmax_kernel<<<Q, 256, 0, st>>>(refined, gh * gw, minmax_ws, minmax_ws + Q);
+        XL_CUDA(launch_pdl(svc_minmax_kernel, dim3(Q), dim3(256), 0, st, refined, gh * gw, minmax_ws, minmax_ws + Q));
         if (int e = check_launch("svc_minmax_kernel")) return e;
     }
     dim3 grid(ceil_div(W, 32), ceil_div(H, 8), B), block(32, 8);
-    svc_upsample_bg_kernel<<<grid, block, 0, st>>>(refined, minmax_ws, minmax_ws + Q, plane_off_dev, gh, gw, H, W, planes);
+    XL_CUDA(launch_pdl(svc_upsample_bg_kernel, dim3(grid), dim3(block), 0, st, refined, minmax_ws, minmax_ws + Q, plane_off_dev, gh, gw, H, W, planes));
     return check_launch("svc_upsample_bg_kernel");
 }

@@ -75,6 +75,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bvec,
                  float* __restrict__ y, __half* __restrict__ ys, int64_t rows, int D, int N,
                  const float* __restrict__ cls, const float* __restrict__ pos) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -190,7 +192,8 @@ struct Ctx {
 };
 
 static int layernorm(const Ctx& c, const float* x, const float* w, const float* b, __half* ys) {
-    layernorm_kernel<false><<<(unsigned)ceil_div64(c.BN, 8), 256, 0, c.st>>>(x, w, b, nullptr, ys, c.BN, c.D, 1, nullptr, nullptr);
+    XL_CUDA(launch_pdl(layernorm_kernel<false>, dim3((unsigned)ceil_div64(c.BN, 8)), dim3(256), 0, c.st, x, w, b, nullptr, ys, c.BN, c.D, 1,
+                       nullptr, nullptr));
     return check_launch("layernorm_kernel");
 }
 
