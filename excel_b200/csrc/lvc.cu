@@ -12,20 +12,23 @@
 namespace xl {
 
 // qt[b, m, c] = f[b, c, m] / max(||f[b, :, m]||, 1e-12): normalise over channels and transpose to [n_p, C].
-// A block of 32 x 8 threads owns 32 positions: channel norms with coalesced reads along m (fixed summation order: channel
-// c in slice c % 8, slices combined 0..7), then 32 x 32 tiles transposed through shared memory so that the writes are
-// coalesced along c.
+// A block of 32 x 8 threads owns 32 positions and the channel slice blockIdx.z (of gridDim.z): channel norms over ALL channels
+// with coalesced reads along m (fixed summation order: channel c in slice c % 8, slices combined 0..7 -- every z-slice computes
+// the same norm), then its 32 x 32 tiles transposed through shared memory so that the writes are coalesced along c.  The channel
+// split exists for small batches: one image of 1024 positions is 32 blocks without it.
 __global__ void __launch_bounds__(256)
 lvc_normalize_t_kernel(const float* __restrict__ f, int C, int np, float* __restrict__ qt) {
     __shared__ float part[8][33], tile[32][33], inv[32];
     const int tx = threadIdx.x, ty = threadIdx.y, m0 = blockIdx.x * 32, b = blockIdx.y;
     const float* src = f + (int64_t)b * C * np;
     float ss = 0.f;
-    if (m0 + tx < np)
+    if (m0 + tx < np) {
+#pragma unroll 8
         for (int c = ty; c < C; c += 8) {
             const float v = src[(int64_t)c * np + m0 + tx];
             ss = fmaf(v, v, ss);
         }
+    }
     part[ty][tx] = ss;
     __syncthreads();
     if (ty == 0) {
@@ -35,7 +38,9 @@ lvc_normalize_t_kernel(const float* __restrict__ f, int C, int np, float* __rest
         inv[tx] = 1.f / fmaxf(sqrtf(t), 1e-12f);
     }
     __syncthreads();
-    for (int c0 = 0; c0 < C; c0 += 32) {
+    const int cper = ((C + 31) / 32 + gridDim.z - 1) / gridDim.z * 32;   // channels per z-slice (multiple of 32)
+    const int cbeg = blockIdx.z * cper, cend = min(C, cbeg + cper);
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = c0 + ty + 8 * k;
@@ -129,7 +134,10 @@ __global__ void centred_sigmoid_kernel(float* __restrict__ x, int64_t n, const f
 // normalise + similarity + batch mean, shared by the LVC bias and attn_pred: sim [B,np,np] and mean_ws[0]
 static int cosine_similarity_and_mean(const float* feats, int B, int C, int np, float* qt_ws, double* rowsum_ws, float* mean_ws,
                                       float* sim, cudaStream_t st) {
-    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 32), B), dim3(32, 8), 0, st>>>(feats, C, np, qt_ws);
+    // channel slices so that a small batch still fills the chip (>= ~2 blocks per SM), at most one slice per 32 channels
+    int zs = 1;
+    while (zs < 8 && ceil_div(np, 32) * B * zs < 2 * kNumSMs && zs * 2 * 32 <= C) zs *= 2;
+    lvc_normalize_t_kernel<<<dim3(ceil_div(np, 32), B, zs), dim3(32, 8), 0, st>>>(feats, C, np, qt_ws);
     if (int e = check_launch("lvc_normalize_t_kernel")) return e;
     // sim[b] = qt[b] qt[b]^T  (exact fp32)
     if (int e = sgemm2(qt_ws, qt_ws, sim, nullptr, nullptr, np, np, C, C, C, np, B, (int64_t)np * C, (int64_t)np * C,
