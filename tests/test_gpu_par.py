@@ -46,6 +46,26 @@ def test_par_vs_oracle(shape):
         assert (out - ref).abs().max() < 2e-5 * 1.01 ** iters, (iters, group)
 
 
+def test_par_affinity_degenerate_neighbourhoods():
+    """utils/PAR.py:67-86 on inputs where the neighbour std vanishes or explodes: constant regions (std = 0 -> the 1e-8 epsilon
+    decides), an isolated spike in a flat region (all 48 differences equal and huge after the division), a step edge and a
+    large-magnitude image.  The kernel folds 1 / ((std + eps) w1) into one squared weight per channel and exponentiates with the
+    bare MUFU: everything must stay finite and equal to the oracle."""
+    from excel_b200.par import par_affinity
+    h, w = 96, 80
+    img = torch.zeros(3, 3, h, w)
+    img[0, :, 40, 30] = 1.0                       # spike in a constant image
+    img[0, 1, 10, 10] = -3.0
+    img[1, :, :, w // 2:] = 2.5                   # step edge, flat on both sides
+    img[1, 0, h // 2:, :] += 1e-4                 # and a barely visible one
+    img[2] = 1e3 * synth.images(1, 96, seed=5)[0, :, :h, :w]
+    aff = par_affinity(img.cuda(), (h, w), port.PAR_DILATIONS).cpu()
+    ref = port.par_affinity(img, (h, w))
+    assert torch.isfinite(aff).all()
+    assert (aff - ref).abs().max() < 5e-6
+    assert (aff.sum(1) - 1.01).abs().max() < 1e-5   # softmax over the 48 neighbours + w2 * positional softmax
+
+
 def test_par_other_dilations_and_strided_image():
     from excel_b200.par import PAR
     imgs = synth.images(2, 80, seed=3)
