@@ -23,6 +23,15 @@
 #include "excel_b200.h"
 #include "tc.cuh"
 
+// Timing experiments on the statistics pass (tools/experiments/stats_probe.py: private builds with -DXL_TUNING
+// -DXL_TC_VARIANT=<mask>; the product build defines neither and every XL_TC(bit) is the constant false):
+//   1 no MUFU.EX2   2 no tcgen05.ld   4 no S MMAs
+#if defined(XL_TUNING) && defined(XL_TC_VARIANT)
+#define XL_TC(bit) (((XL_TC_VARIANT) & (bit)) != 0)
+#else
+#define XL_TC(bit) false
+#endif
+
 namespace xl {
 
 constexpr int kABK = 64;                                  // head dim == one 64-wide k block
@@ -162,6 +171,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint64_t a_hi = umma_desc_sw128(xa), a_lo = umma_desc_sw128(xa + kATile);
                 const uint64_t b_hi = umma_desc_sw128(yb), b_lo = umma_desc_sw128(yb + kATile);
                 if (leader) {
+                    if (!(XL_TC(4) && MODE == 0))
 #pragma unroll
                     for (int k = 0; k < kABK / 16; ++k) {
                         const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -225,6 +235,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     for (int c = 0; c < 2; ++c) {
                         const int key0 = kb * 128 + cq * 64 + c * 32;
                         uint32_t r[32];
+                        if (XL_TC(2)) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) r[e] = 0x3c000000u + (uint32_t)(lane + e + c);
+                        } else
                         if (!TAIL || key0 < p.N)   // (uniform) else: padding keys only -- not even computed by the MMA
                             tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * 128 + cq * 64 + c * 32), r);
                         if (c == 1) {     // this warp's TMEM reads of the tile are done
@@ -257,8 +271,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             for (int e = 0; e < 32; e += 4) {
                                 const float2 xa = __ffma2_rn(al, make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), mm);
                                 const float2 xb = __ffma2_rn(al, make_float2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), mm);
-                                sa = __fadd2_rn(sa, make_float2(ex2_approx(xa.x), ex2_approx(xa.y)));
-                                sb = __fadd2_rn(sb, make_float2(ex2_approx(xb.x), ex2_approx(xb.y)));
+                                sa = __fadd2_rn(sa, XL_TC(1) ? xa : make_float2(ex2_approx(xa.x), ex2_approx(xa.y)));
+                                sb = __fadd2_rn(sb, XL_TC(1) ? xb : make_float2(ex2_approx(xb.x), ex2_approx(xb.y)));
                             }
                             l_run = l_run * ex2_approx(m_run - m_new) + ((sa.x + sb.x) + (sa.y + sb.y));
                             m_run = m_new;
