@@ -295,7 +295,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     bar_sync(team_bar, 128);
                     if (leader) {
                         if (p.C) {
-                            tma_store_4d(&tmC, sb, nb, m0, z2, z1);
+                            if (p.c_add) tma_reduce_add_4d(&tmC, sb, nb, m0, z2, z1);
+                            else tma_store_4d(&tmC, sb, nb, m0, z2, z1);
                         } else {
                             const int col = z2 * (int)p.cs2 + nb;
                             tma_store_3d(&tmS, sb, col, m0, z1);
@@ -453,6 +454,7 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
             tma_epi = true;
         }
     }
+    XL_REQUIRE(!p.c_add || (tma_epi && p.C && !p.residual), "tc_gemm: C += needs an fp32 output that TMA can address and no residual");
     const bool res = tma_epi && p.C != nullptr && p.residual != nullptr;   // (the non-TMA fallback epilogue reads the residual itself)
 #define XL_TC_LAUNCH(BN_, EPI_, RES_) \
     XL_CUDA(launch_pdl(gemm_tc_kernel<BN_, EPI_, RES_>, dim3(grid), dim3(kTcThreads), tc_smem(BN_), st, tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total))

@@ -21,6 +21,8 @@ struct TcParams {
     const float* bias;          // [N] or null; batch z1 uses bias + z1 * bias1
     int64_t bias1;
     const float* residual;      // same layout as C, or null (may alias C)
+    int c_add;                  // C += ... : the fp32 tile leaves as a TMA reduce-add (the add is performed in L2) -- the in-place
+                                // residual update without reading the residual in the epilogue; needs the TMA-store layout rules
     float alpha;
     int act;                    // 0 none, 1 QuickGELU
     __half* Cs;                 // split-fp16 output (may be null): hi at Cs, lo at Cs + cs_lo_off

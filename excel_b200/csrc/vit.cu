@@ -150,7 +150,7 @@ __global__ void copy_cls_kernel(const float* __restrict__ src, float* __restrict
 }
 
 struct Ws {  // workspace carve-up
-    float *pos, *m, *pnew, *part, *mid, *x0;
+    float *pos, *m, *pnew, *part, *x0;
     __half *col, *h, *qkv, *pn, *o, *o2, *u;
 };
 
@@ -170,7 +170,7 @@ static size_t ws_bytes(int B, int N, int D, int H, int KKp) {
     t += align256((size_t)3 * B * H * N * 4);         // softmax row statistic (up to 3 score sets)
     t += align256((size_t)B * N * ((N + 3) & ~3) * 4); // pnew (row-padded new-path map: LVC branch only)
     t += align256(part_bytes(B, N, H));               // part
-    t += 2 * align256(BN * D * 4);                    // mid, x0
+    t += align256(BN * D * 4);                        // x0
     t += align256((size_t)B * (N - 1) * 2 * KKp * 2); // col
     t += align256(BN * 2 * D * 2) + align256(2 * BN * 2 * D * 2);   // h; o2 | o
     t += align256(BN * 6 * D * 2);                    // qkv
@@ -203,10 +203,15 @@ struct Wt { const void* ws; float scale; };
 
 // y = act(x W^T + bias) (+ residual): x split [M rows per batch, 2K] (map ma), W split [Nout, 2K].
 // batch = 2 runs two activations (row blocks a_row1 apart in ma) against the SAME weights into outputs c1 floats apart.
+// residual == y (an in-place update) leaves as TMA reduce-adds: the epilogue then never waits for residual loads (a quarter of
+// the stall samples of the residual GEMMs) and the add happens once, in fp32, in L2 -- the same single rounding.
 static int linear(const Ctx& c, const CUtensorMap& ma, Wt w, int K, int Nout, const float* bias, int act,
                   const float* residual, float* y, __half* ys, int batch = 1, int64_t c1 = 0) {
     TcParams p = {};
     p.M = (int)c.BN; p.N = Nout; p.kblocks = K / 64; p.a_lo_off = K; p.b_lo_off = K; p.nb2 = 1;
+    const bool in_place = residual != nullptr && residual == y && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && Nout % 4 == 0 &&
+                          (batch == 1 || c1 % 4 == 0);
+    if (in_place) { residual = nullptr; p.c_add = 1; }
     p.C = y; p.ldc = Nout; p.bias = bias; p.residual = residual; p.alpha = 1.f / w.scale; p.act = act;
     p.Cs = ys; p.lds = 2 * Nout; p.cs_lo_off = Nout;
     if (batch > 1) { p.a_row1 = (int)c.BN; p.c1 = c1; }
@@ -304,7 +309,6 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         c.w.m = (float*)take((size_t)3 * B * H * N * 4);
         c.w.pnew = (float*)take((size_t)B * N * Npad * 4);
         c.w.part = (float*)take(part_bytes(B, N, H));
-        c.w.mid = (float*)take(BN * D * 4);
         c.w.x0 = (float*)take(BN * D * 4);
         c.w.col = (__half*)take((size_t)B * npatch * 2 * KKp * 2);
         c.w.h = (__half*)take(BN * 2 * D * 2);
@@ -363,8 +367,8 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
         if (l < first) {  // ---- standard block (:332-337)
             if (int e = qkv_stage(c, x, Lw)) return e;
             if (int e = attention_qk(c, scale, attn_l, 1.f / H)) return e;    // need_weights: head mean; o = attn @ v
-            if (int e = linear(c, c.m.o, w_out, D, D, Lw.out_b, 0, x, c.w.mid, nullptr)) return e;       // x + attn
-            if (int e = mlp_stage(c, c.w.mid, Lw, feat_l)) return e;
+            if (int e = linear(c, c.m.o, w_out, D, D, Lw.out_b, 0, x, feat_l, nullptr)) return e;         // x + attn, into this block's slot
+            if (int e = mlp_stage(c, feat_l, Lw, feat_l)) return e;                                      // += MLP, in place
             x = feat_l;
         } else {  // ---- surgery block (:309-330, Attention.forward :95-159)
             float* xnew = feats + (int64_t)(first - 1) * BN * D;              // new path, accumulates x_res in place
@@ -394,7 +398,7 @@ extern "C" int excel_vit_forward(const ExcelVitWeights* Wt, const float* img, in
             if (int e = attention_qk(c, scale, attn_l, 1.f)) return e;          // x_ori = attn_ori @ v
             // mid = src + proj(x_ori): a separate buffer for the first surgery block, in place afterwards
             // (the reference's `x_ori += x_ori_res` mutates the view it stored in all_feats[l-1], :317)
-            float* mid = (l == first) ? c.w.mid : src;
+            float* mid = (l == first) ? feat_l : src;   // first surgery block: into its own slot, then the MLP updates it in place
             if (l == first) {   // src IS xnew here: the two products read / update the same rows, so they stay two launches
                 if (int e = linear(c, c.m.o, w_out, D, D, Lw.out_b, 0, src, mid, nullptr)) return e;
                 if (int e = linear(c, c.m.o2, w_out, D, D, Lw.out_b, 0, xnew, xnew, nullptr)) return e;   // x += x_res (:319,329)
