@@ -456,6 +456,10 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
     }
     XL_REQUIRE(!p.c_add || (tma_epi && p.C && !p.residual), "tc_gemm: C += needs an fp32 output that TMA can address and no residual");
     const bool res = tma_epi && p.C != nullptr && p.residual != nullptr;   // (the non-TMA fallback epilogue reads the residual itself)
+    // 256-wide tiles with a K-major B: CTA pairs (M = 256) fetch a third less from L2 per MMA, which is what bounds these shapes
+    if (bn == 256 && tma_epi && !p.b_mn && p.N % 256 == 0 &&
+        (int64_t)(p.N / 256) * ((tiles_m + 1) / 2) * batch >= kNumSMs / 2)
+        return tc_gemm_pair(tmA, tmB, tmC, tmS, p, batch, res, st);
 #define XL_TC_LAUNCH(BN_, EPI_, RES_) \
     XL_CUDA(launch_pdl(gemm_tc_kernel<BN_, EPI_, RES_>, dim3(grid), dim3(kTcThreads), tc_smem(BN_), st, tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total))
 #define XL_TC_PICK(BN_) \

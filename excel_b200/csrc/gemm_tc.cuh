@@ -36,6 +36,9 @@ struct TcParams {
 // box_rows = 128 for an A operand, = the tile N (64 or 128) for a B operand
 int make_operand_map(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols_total, int64_t ld_elems, int box_rows);
 int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int batch, int bn, cudaStream_t st);
+// 256-wide tiles on CTA pairs (gemm_tc2.cu: tcgen05 cta_group::2, M = 256): chosen by tc_gemm when the shape fills the chip
+int tc_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmS, const TcParams& p,
+                 int batch, bool res, cudaStream_t st);
 int tc_pick_bn(int64_t M, int N, int batch);   // tile width (64 / 128 / 256) by tile count
 // x [rows, cols] fp32 (pitch ldx) -> out [rows, 2*Kp] fp16 (hi | lo), zero padded; Kp % 64 == 0
 int split_f16(const float* x, int64_t ldx, int rows, int cols, int Kp, __half* out, cudaStream_t st, float scale = 1.f);
