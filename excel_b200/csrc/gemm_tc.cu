@@ -457,9 +457,13 @@ int tc_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, i
     XL_REQUIRE(!p.c_add || (tma_epi && p.C && !p.residual), "tc_gemm: C += needs an fp32 output that TMA can address and no residual");
     const bool res = tma_epi && p.C != nullptr && p.residual != nullptr;   // (the non-TMA fallback epilogue reads the residual itself)
     // 256-wide tiles with a K-major B: CTA pairs (M = 256) fetch a third less from L2 per MMA, which is what bounds these shapes
-    if (bn == 256 && tma_epi && !p.b_mn && p.N % 256 == 0 &&
-        (int64_t)(p.N / 256) * ((tiles_m + 1) / 2) * batch >= kNumSMs / 2)
-        return tc_gemm_pair(tmA, tmB, tmC, tmS, p, batch, res, st);
+    // -- when their rounds cost less than the single-CTA waves: a pair tile takes ~0.9 of a single tile's time (measured), but
+    // pair tiles quantise on 74 pairs (odd row-block counts add a ghost block per batch item)
+    if (bn == 256 && tma_epi && !p.b_mn && p.N % 256 == 0) {
+        const int64_t ptiles = (int64_t)(p.N / 256) * ((tiles_m + 1) / 2) * batch;
+        const int64_t rounds_pair = ceil_div64(ptiles, kNumSMs / 2), waves_single = ceil_div64(total, kNumSMs);
+        if (ptiles >= kNumSMs / 2 && 9 * rounds_pair < 10 * waves_single) return tc_gemm_pair(tmA, tmB, tmC, tmS, p, batch, res, st);
+    }
 #define XL_TC_LAUNCH(BN_, EPI_, RES_) \
     XL_CUDA(launch_pdl(gemm_tc_kernel<BN_, EPI_, RES_>, dim3(grid), dim3(kTcThreads), tc_smem(BN_), st, tmA, tmB, tmC, tmS, p, tiles_n, tiles_m, (int)total))
 #define XL_TC_PICK(BN_) \
