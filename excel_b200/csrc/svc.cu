@@ -89,10 +89,24 @@ svc_rowpass_kernel(const float* __restrict__ A, const int* __restrict__ img_of, 
     const float* xq = x ? x + (int64_t)q * np : nullptr;
     const float* sib = si ? si + (int64_t)b * np : nullptr;
     float s = 0.f;
-    for (int j = lane; j < np; j += 32) {
-        float v = xq ? xq[j] : 1.f;
-        if (sib) v *= sib[j];
-        s = fmaf(__ldg(row + j), v, s);
+    if ((np & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(xq) | reinterpret_cast<uintptr_t>(sib)) & 15) == 0) {
+        // 16 B loads, every load of the row in flight at once (n_p = 1024: eight per lane); lane-local order j, j+1, j+2, j+3
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        const float4* x4 = reinterpret_cast<const float4*>(xq);
+        const float4* s4 = reinterpret_cast<const float4*>(sib);
+#pragma unroll 8
+        for (int j = lane; j < np / 4; j += 32) {
+            const float4 a = __ldg(r4 + j);
+            float4 v = x4 ? x4[j] : make_float4(1.f, 1.f, 1.f, 1.f);
+            if (s4) { const float4 w = s4[j]; v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w; }
+            s = fmaf(a.x, v.x, s); s = fmaf(a.y, v.y, s); s = fmaf(a.z, v.z, s); s = fmaf(a.w, v.w, s);
+        }
+    } else {
+        for (int j = lane; j < np; j += 32) {
+            float v = xq ? xq[j] : 1.f;
+            if (sib) v *= sib[j];
+            s = fmaf(__ldg(row + j), v, s);
+        }
     }
     s = warp_sum(s);
     if (lane == 0) {
@@ -119,6 +133,7 @@ svc_colpass_kernel(const float* __restrict__ A, const int* __restrict__ img_of, 
     const float* sib = si ? si + (int64_t)b * np : nullptr;
     float s = 0.f;
     if (j < np) {
+#pragma unroll 8
         for (int i = ry; i < np; i += 32) {
             float v = xq ? xq[i] : 1.f;
             if (sib) v *= sib[i];
