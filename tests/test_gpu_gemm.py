@@ -105,3 +105,24 @@ def test_split_engine_real_checkpoint_magnitudes(sigma):
     ref2 = A2.double() @ Wt.double().t()
     assert torch.isfinite(C).all()
     assert ((C.double() - ref2).abs() / (A2.abs().double() @ Wt.abs().double().t())).max() < 5e-4   # lo alone carries the excess: 11 bits
+
+
+@pytest.mark.parametrize("shape", [(9500, 768, 768), (128 * 75 + 1, 1024, 320), (16400, 256, 3072)])
+def test_gemm_tc_cta_pairs(shape):
+    """Shapes whose 256-wide tiles give at least one pair tile per TPC run on CTA pairs (gemm_tc2.cu: cta_group::2, M = 256):
+    odd row-block counts (a ghost block in the last pair), rows that end inside a block, bias / activation / residual epilogues
+    -- against float64."""
+    M, N, K = shape
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    x = A.double() @ B.double().t()
+    for kwargs, ref in (({}, x), ({"bias": bias, "residual": res}, x + bias.double() + res.double()),
+                        ({"bias": bias, "alpha": 0.5, "act": 1}, None)):
+        if ref is None:
+            y = 0.5 * x + bias.double()
+            ref = y * torch.sigmoid(1.702 * y)
+        C = _tc(A, B, **kwargs)
+        assert (C.double() - ref).abs().max().item() / ref.abs().max().item() < 3e-5, (shape, kwargs.keys())
